@@ -1,0 +1,191 @@
+/*
+ * read_b200 — C ABI of the B200-native READ render hot path.
+ *
+ * Plain C: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ * All data pointers are CALLER-OWNED DEVICE memory unless a parameter is named
+ * `*_host`.  Every launch is asynchronous on the caller's stream (`stream` is a
+ * cudaStream_t passed as void*); no entry point synchronises the device,
+ * allocates per call, or touches the host copy of the data.
+ *
+ * Return value: 0 on success, negative error code otherwise;
+ * read_last_error() returns a thread-local message (the Python host raises
+ * RuntimeError with it, matching the reference's AT_ASSERTM -> RuntimeError
+ * behaviour, pcpr_cuda.cpp:17-21).
+ *
+ * Which reference interface each entry point replaces is cited per function
+ * (paths relative to the JOP-Lee/READ tree).
+ */
+#ifndef READ_B200_H
+#define READ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define READ_MAX_LEVELS 8
+#define READ_MAX_SRC 4
+
+enum {
+    READ_OK = 0,
+    READ_ERR_INVALID = -1,   /* bad argument (shape, alignment, null)            */
+    READ_ERR_CUDA = -2,      /* CUDA runtime / driver error, see read_last_error */
+    READ_ERR_UNSUPPORTED = -3
+};
+
+int read_version(void);
+const char *read_last_error(void);
+/* 1 if the current device is sm_100 (B200); the library refuses to launch elsewhere. */
+int read_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rasterizer.  Packed z-buffer entry: (uint64)float_bits(depth) << 32 | point_id ;
+ * empty = 0x7FFFFFFFFFFFFFFF (max int64, so signed and unsigned min agree).  atomicMin on it == "min depth, ties -> lowest id", the
+ * sequential semantics of DepthProject (MyRender/CloudProjection/point_render.cu:125-167).
+ * Pyramid layout: level-major; level l holds [B, h_l, w_l] entries, w_l = int(W*0.5^l),
+ * h_l = int(H*0.5^l) (src/READ/gl/myrender.py:33-34).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Number of uint64 entries of a B-view, L-level pyramid (size your zbuf with this). */
+int64_t read_pyramid_entries(int B, int W, int H, int L);
+/* Entry offset of level l inside the pyramid, and its (w,h). */
+int64_t read_pyramid_level_offset(int B, int W, int H, int l);
+void read_level_size(int W, int H, int l, int *w, int *h);
+
+/* Reset a pyramid (or any zbuf) to "empty". */
+int read_zbuf_clear(uint64_t *zbuf, int64_t entries, void *stream);
+
+/*
+ * Replaces: the L calls of pcpr.forward made by MyRender.render
+ * (src/READ/gl/myrender.py:32-40 -> pcpr_cuda.cpp:23-37 -> point_render.cu:169-200),
+ * fused: every point is read, culled and projected ONCE for all B views and all L levels.
+ *   xyz      [n,3] f32 device            total_m [B,16] f32 device, row-major 4x4 (proj @ inv(view))
+ *   zbuf     pyramid of read_pyramid_entries(B,W,H,L) uint64, already cleared
+ *   id_base  added to the local point index to form the global id written in the z-buffer
+ *            (point-sharded multi-GPU rendering: each rank passes its shard's first global id)
+ * Levels whose size is exactly half of the previous one are derived from it by a 2x2 min
+ * (bit-identical to rasterising them directly); the others get direct atomics.
+ */
+int read_raster_project(const float *xyz, int64_t n, int64_t id_base, const float *total_m, int B,
+                        int W, int H, int L, uint64_t *zbuf, void *stream);
+/* Second half of the above when a collective sits in between (multi-GPU): project only the levels
+ * that need direct atomics (read_raster_project_direct), all-reduce(min) them, then derive the rest. */
+int read_raster_project_direct(const float *xyz, int64_t n, int64_t id_base, const float *total_m, int B,
+                               int W, int H, int L, uint64_t *zbuf, void *stream);
+int read_raster_derive_levels(int B, int W, int H, int L, uint64_t *zbuf, void *stream);
+/* Bitmask of levels rasterised with direct atomics (bit l set) for this geometry. */
+unsigned read_raster_direct_mask(int W, int H, int L);
+
+/*
+ * Replaces: the float outputs of GPU_PCPR (point_render.cu:176-177,196-199): for one level,
+ * index [B,h,w] f32 (0 = empty) and depth [B,h,w] f32 (0 = empty) from the packed z-buffer.
+ * Either output may be NULL.
+ */
+int read_zbuf_resolve(const uint64_t *zbuf_level, int64_t pixels, float *index_out, float *depth_out,
+                      void *stream);
+
+/*
+ * Replaces: pcpr.forward itself (pcpr_cuda.cpp:23-37): one level, B views.
+ * zbuf_ws: workspace of B*h*w uint64 (cleared inside).  Outputs as GPU_PCPR.
+ */
+int read_pcpr_forward(const float *xyz, int64_t n, const float *total_m, int B, int w, int h,
+                      uint64_t *zbuf_ws, float *index_out, float *depth_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Descriptor gather (PointTexture, READ/models/texture.py:42-70).
+ * Descriptors live point-major [N, D] ("shadow" of the checkpoint's [1, D, N] parameter) so that
+ * one pixel touches one 32-byte sector (D = 8 f32) instead of 8.
+ * ---------------------------------------------------------------------------------------- */
+
+/* [1,D,N] f32 channel-major  <->  [N,D] f32 point-major. */
+int read_texture_to_point_major(const float *tex_cn, int D, int64_t N, float *tex_nd, void *stream);
+int read_texture_to_channel_major(const float *tex_nd, int D, int64_t N, float *tex_cn, void *stream);
+
+enum { READ_FEAT_NCHW_F32 = 0, READ_FEAT_NHWC_F32 = 1, READ_FEAT_NHWC_BF16 = 2 };
+enum { READ_TEXACT_NONE = 0, READ_TEXACT_SIGMOID = 1, READ_TEXACT_TANH = 2 };
+
+/* From a float index map (API path: PointTexture.forward(ids), texture.py:52-63).
+ * ids [pixels] f32 (channel 0 of the uv input, already contiguous); out [B, D, h, w] or NHWC. */
+int read_gather_from_index(const float *tex_nd, int D, int64_t N, const float *ids, int B, int h, int w,
+                           int layout, int activation, void *out, void *stream);
+/* Fused path: straight from the packed z-buffer level (skips the float index map). */
+int read_gather_from_zbuf(const float *tex_nd, int D, int64_t N, const uint64_t *zbuf_level, int B, int h,
+                          int w, int layout, int activation, void *out, void *stream);
+/* Backward of the gather (autograd of index_select, texture.py:61): grad_tex_nd[ids[p], :] += grad_out[.., p]
+ * grad_out is NCHW f32 [B,D,h,w]; grad_tex_nd [N,D] f32 accumulates (caller zeroes).  Empty pixels carry
+ * id 0, so point 0 receives their gradient exactly like the reference. */
+int read_gather_backward(const float *grad_out, const float *ids, int B, int D, int h, int w, int64_t N,
+                         float *grad_tex_nd, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gated convolution (BasicConv, READ/models/unet.py:22-53) with everything around it fused:
+ *   y = bn_scale * ( A(conv_f(x)+b_f) * sigmoid(conv_m(x)+b_m) ) + bn_shift  [+ residual]
+ * x is a VIRTUAL concat of up to 4 NHWC sources, each resampled on the fly (nearest up/down by an
+ * integer factor = F.interpolate default mode, unet.py:239-250; bilinear x4 align_corners=False =
+ * nn.Upsample, unet.py:200), optionally multiplied elementwise by `mul` (FAM, unet.py:114-117).
+ * ---------------------------------------------------------------------------------------- */
+enum { READ_ACT_F32 = 0, READ_ACT_BF16 = 1 };
+enum { READ_SRC_IDENTITY = 0, READ_SRC_NEAREST_DOWN = 1, READ_SRC_NEAREST_UP = 2, READ_SRC_BILINEAR_UP4 = 3 };
+enum { READ_OUT_NHWC = 0, READ_OUT_NCHW_F32 = 1 };
+enum { READ_CONV_AUTO = 0, READ_CONV_GENERIC = 1, READ_CONV_TCGEN05 = 2 };
+
+typedef struct read_src {
+    const void *ptr;   /* [B, H, W, C] NHWC, activation dtype */
+    int32_t C, H, W;
+    int32_t mode;      /* READ_SRC_* */
+    int32_t factor;    /* resample factor for NEAREST_* (2,4,8); ignored otherwise */
+} read_src;
+
+typedef struct read_conv_desc {
+    int32_t act_dtype;              /* READ_ACT_* : storage type of sources / residual / NHWC out */
+    int32_t n_src;
+    read_src src[READ_MAX_SRC];
+    const void *mul;                /* optional [B,Hin,Win,Cin], only with n_src==1 identity */
+    int32_t B, Hin, Win, Cin;       /* logical (post-resample, post-concat) input */
+    int32_t Hout, Wout, Cout;
+    int32_t k, stride, pad;
+    int32_t elu;                    /* 1: A = ELU(alpha=1); 0: identity */
+    const float *w_generic;         /* packed f32 [k*k*Cin][Npad] (read_pack_weights_generic) or NULL */
+    const void *w_tc;               /* packed bf16 for the tcgen05 kernel (read_pack_weights_tc) or NULL */
+    const float *bias_f, *bias_m;   /* [Cout] */
+    const float *bn_scale, *bn_shift; /* [Cout] folded eval-mode BatchNorm */
+    const void *residual;           /* optional [B,Hout,Wout,Cout] added after BN (ResBlock / FAM skip) */
+    void *out;
+    int32_t out_mode;               /* READ_OUT_* */
+    void *out2;                     /* optional second NHWC output: out2 = y * out2_mul (feeds a FAM) */
+    const void *out2_mul;
+    int32_t impl;                   /* READ_CONV_* request */
+} read_conv_desc;
+
+typedef struct read_conv_plan read_conv_plan;
+
+/* Npad of the generic packing for a given Cout (multiple of 32, f|m halves per 32-channel group). */
+int read_generic_npad(int Cout);
+/* Pack torch-layout weights [Cout,Cin,k,k] f32 (device) into the kernel layouts (device). */
+int read_pack_weights_generic(const float *wf, const float *wm, int Cout, int Cin, int k, float *out,
+                              void *stream);
+int64_t read_tc_weight_elems(int Cout, int Cin, int k);
+int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16,
+                         void *stream);
+/* 1 if the tcgen05 kernel supports this layer (shape/dtype), else 0 (-> generic CUDA-core kernel). */
+int read_conv_tc_supported(const read_conv_desc *d);
+
+/* Plan = validated descriptor + chosen kernel + TMA tensor maps.  Host-side only, no device work. */
+int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out);
+int read_conv_plan_launch(const read_conv_plan *p, void *stream);
+int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC or READ_CONV_TCGEN05 */
+void read_conv_plan_destroy(read_conv_plan *p);
+
+/* Layout converters at the net boundary. */
+int read_nchw_f32_to_nhwc(const float *in, int B, int C, int H, int W, int act_dtype, void *out, void *stream);
+int read_nhwc_to_nchw_f32(const void *in, int act_dtype, int B, int C, int H, int W, float *out, void *stream);
+
+/* Counts kernels launched by this library since load (bench.py's gpu_launches claim). */
+int64_t read_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* READ_B200_H */

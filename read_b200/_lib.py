@@ -1,0 +1,129 @@
+"""ctypes binding of the C-ABI library (include/read_b200.h).
+
+The product path fails LOUDLY when the CUDA library is missing or the device is not a B200:
+there is no CPU or eager-PyTorch fallback anywhere in this package.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libread_b200.so")
+
+c_int, c_i64, c_u32 = ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
+c_vp = ctypes.c_void_p
+
+MAX_SRC = 4
+
+# enums (mirror include/read_b200.h)
+FEAT_NCHW_F32, FEAT_NHWC_F32, FEAT_NHWC_BF16 = 0, 1, 2
+TEXACT = {"none": 0, "sigmoid": 1, "tanh": 2}
+ACT_F32, ACT_BF16 = 0, 1
+SRC_IDENTITY, SRC_NEAREST_DOWN, SRC_NEAREST_UP, SRC_BILINEAR_UP4 = 0, 1, 2, 3
+OUT_NHWC, OUT_NCHW_F32 = 0, 1
+CONV_AUTO, CONV_GENERIC, CONV_TCGEN05 = 0, 1, 2
+
+
+class ReadSrc(ctypes.Structure):
+    _fields_ = [("ptr", c_vp), ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("mode", ctypes.c_int32), ("factor", ctypes.c_int32)]
+
+
+class ReadConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("act_dtype", ctypes.c_int32), ("n_src", ctypes.c_int32), ("src", ReadSrc * MAX_SRC),
+        ("mul", c_vp),
+        ("B", ctypes.c_int32), ("Hin", ctypes.c_int32), ("Win", ctypes.c_int32), ("Cin", ctypes.c_int32),
+        ("Hout", ctypes.c_int32), ("Wout", ctypes.c_int32), ("Cout", ctypes.c_int32),
+        ("k", ctypes.c_int32), ("stride", ctypes.c_int32), ("pad", ctypes.c_int32), ("elu", ctypes.c_int32),
+        ("w_generic", c_vp), ("w_tc", c_vp),
+        ("bias_f", c_vp), ("bias_m", c_vp), ("bn_scale", c_vp), ("bn_shift", c_vp),
+        ("residual", c_vp), ("out", c_vp), ("out_mode", ctypes.c_int32),
+        ("out2", c_vp), ("out2_mul", c_vp), ("impl", ctypes.c_int32),
+    ]
+
+
+_SIGS = {
+    "read_version": (c_int, []),
+    "read_last_error": (ctypes.c_char_p, []),
+    "read_device_ok": (c_int, []),
+    "read_pyramid_entries": (c_i64, [c_int, c_int, c_int, c_int]),
+    "read_pyramid_level_offset": (c_i64, [c_int, c_int, c_int, c_int]),
+    "read_level_size": (None, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "read_zbuf_clear": (c_int, [c_vp, c_i64, c_vp]),
+    "read_raster_project": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_raster_project_direct": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_raster_derive_levels": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_raster_direct_mask": (c_u32, [c_int, c_int, c_int]),
+    "read_zbuf_resolve": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "read_pcpr_forward": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "read_texture_to_point_major": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "read_texture_to_channel_major": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "read_gather_from_index": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_gather_from_zbuf": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_gather_backward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp]),
+    "read_generic_npad": (c_int, [c_int]),
+    "read_pack_weights_generic": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_tc_weight_elems": (c_i64, [c_int, c_int, c_int]),
+    "read_pack_weights_tc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_conv_tc_supported": (c_int, [ctypes.POINTER(ReadConvDesc)]),
+    "read_conv_plan_create": (c_int, [ctypes.POINTER(ReadConvDesc), ctypes.POINTER(c_vp)]),
+    "read_conv_plan_launch": (c_int, [c_vp, c_vp]),
+    "read_conv_plan_impl": (c_int, [c_vp]),
+    "read_conv_plan_destroy": (None, [c_vp]),
+    "read_nchw_f32_to_nhwc": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_nhwc_to_nchw_f32": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_launch_count": (c_i64, []),
+}
+
+EXPORTS = tuple(sorted(_SIGS))
+_lib = None
+
+
+def load():
+    """Load libread_b200.so (built by ``python -m read_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"read_b200: CUDA library not built ({LIB_PATH} missing). Run `python -m read_b200.build`. "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().read_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"read_b200: {msg} (code {rc})")
+
+
+_device_checked = set()
+
+
+def require_device(device_index=None):
+    """Raise unless torch sees a CUDA device of compute capability 10.x (B200)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("read_b200: no CUDA device; this package has no CPU fallback")
+    idx = torch.cuda.current_device() if device_index is None else device_index
+    if idx in _device_checked:
+        return
+    major, _ = torch.cuda.get_device_capability(idx)
+    if major != 10:
+        raise RuntimeError(f"read_b200: kernels are built for sm_100a only, device {idx} is sm_{major}x")
+    _device_checked.add(idx)
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,145 @@
+// C-ABI glue: error state, device checks, conv plan dispatch.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include <mutex>
+#include <new>
+
+namespace rb {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms()
+{
+    // per-device cache (DataParallel drives several devices from one process)
+    static std::mutex mu;
+    static int cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+struct read_conv_plan {
+    read_conv_desc d;
+    int impl;
+    TcPlan *tc;
+};
+
+static int validate_conv(const read_conv_desc &d)
+{
+    RB_CHECK_ARG(d.act_dtype == READ_ACT_F32 || d.act_dtype == READ_ACT_BF16, "conv: bad act_dtype");
+    RB_CHECK_ARG(d.n_src >= 1 && d.n_src <= READ_MAX_SRC, "conv: 1..%d sources", READ_MAX_SRC);
+    RB_CHECK_ARG(d.k == 1 || d.k == 3 || d.k == 4, "conv: kernel size must be 1, 3 or 4");
+    RB_CHECK_ARG(d.stride == 1 || d.stride == 2, "conv: stride must be 1 or 2");
+    RB_CHECK_ARG(d.B >= 1 && d.Hin >= 1 && d.Win >= 1 && d.Cout >= 1, "conv: bad shape");
+    int csum = 0;
+    for (int i = 0; i < d.n_src; ++i) {
+        const read_src &s = d.src[i];
+        RB_CHECK_ARG(s.ptr != nullptr, "conv: source %d is null", i);
+        RB_CHECK_ARG(s.C >= 8 && s.C % 8 == 0, "conv: source channels must be a multiple of 8 (got %d)", s.C);
+        RB_CHECK_ARG((reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0, "conv: source %d must be 16B aligned", i);
+        int eh = s.H, ew = s.W;
+        switch (s.mode) {
+        case READ_SRC_IDENTITY: break;
+        case READ_SRC_NEAREST_DOWN:
+            RB_CHECK_ARG(s.factor >= 2, "conv: bad resample factor");
+            eh = s.H / s.factor; ew = s.W / s.factor; break;
+        case READ_SRC_NEAREST_UP:
+            RB_CHECK_ARG(s.factor >= 2, "conv: bad resample factor");
+            eh = s.H * s.factor; ew = s.W * s.factor; break;
+        case READ_SRC_BILINEAR_UP4: eh = s.H * 4; ew = s.W * 4; break;
+        default: RB_CHECK_ARG(false, "conv: unknown source mode %d", s.mode);
+        }
+        RB_CHECK_ARG(eh == d.Hin && ew == d.Win, "conv: source %d resamples to %dx%d, expected %dx%d", i, eh, ew, d.Hin, d.Win);
+        csum += s.C;
+    }
+    RB_CHECK_ARG(csum == d.Cin, "conv: sources hold %d channels, Cin is %d", csum, d.Cin);
+    RB_CHECK_ARG(d.mul == nullptr || (d.n_src == 1 && d.src[0].mode == READ_SRC_IDENTITY), "conv: mul needs one identity source");
+    const int eh = (d.Hin + 2 * d.pad - d.k) / d.stride + 1, ew = (d.Win + 2 * d.pad - d.k) / d.stride + 1;
+    RB_CHECK_ARG(eh == d.Hout && ew == d.Wout, "conv: output is %dx%d, expected %dx%d", d.Hout, d.Wout, eh, ew);
+    RB_CHECK_ARG(d.bias_f && d.bias_m && d.bn_scale && d.bn_shift && d.out, "conv: null parameter pointer");
+    RB_CHECK_ARG(d.out_mode == READ_OUT_NHWC || d.out_mode == READ_OUT_NCHW_F32, "conv: bad out_mode");
+    RB_CHECK_ARG((d.out2 == nullptr) == (d.out2_mul == nullptr), "conv: out2 and out2_mul come together");
+    RB_CHECK_ARG(d.out2 == nullptr || d.out_mode == READ_OUT_NHWC, "conv: out2 needs NHWC output");
+    return READ_OK;
+}
+
+extern "C" {
+
+int read_version(void) { return 100; }
+const char *read_last_error(void) { return g_err; }
+int64_t read_launch_count(void) { return g_launches.load(); }
+
+int read_device_ok(void)
+{
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+int read_conv_tc_supported(const read_conv_desc *d)
+{
+    if (!d) return 0;
+    return tc_supported(*d) ? 1 : 0;
+}
+
+int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out)
+{
+    RB_CHECK_ARG(d && out, "conv plan: null argument");
+    int rc = validate_conv(*d);
+    if (rc) return rc;
+    int impl = d->impl;
+    if (impl == READ_CONV_AUTO) impl = (d->w_tc && tc_supported(*d)) ? READ_CONV_TCGEN05 : READ_CONV_GENERIC;
+    if (impl == READ_CONV_TCGEN05) {
+        RB_CHECK_ARG(d->w_tc != nullptr, "conv plan: tcgen05 requested without packed bf16 weights");
+        if (!tc_supported(*d)) { set_error("conv plan: layer shape not supported by the tcgen05 kernel"); return READ_ERR_UNSUPPORTED; }
+    } else {
+        RB_CHECK_ARG(d->w_generic != nullptr, "conv plan: generic kernel needs w_generic");
+        RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d->w_generic) & 15) == 0, "conv plan: w_generic must be 16B aligned");
+    }
+    read_conv_plan *p = new (std::nothrow) read_conv_plan{*d, impl, nullptr};
+    RB_CHECK_ARG(p != nullptr, "conv plan: out of host memory");
+    if (impl == READ_CONV_TCGEN05) {
+        rc = tc_plan_create(*d, &p->tc);
+        if (rc) { delete p; return rc; }
+    }
+    *out = p;
+    return READ_OK;
+}
+
+int read_conv_plan_launch(const read_conv_plan *p, void *stream)
+{
+    RB_CHECK_ARG(p != nullptr, "conv plan: null plan");
+    if (p->impl == READ_CONV_TCGEN05) return tc_plan_launch(p->tc, (cudaStream_t)stream);
+    return launch_generic(p->d, (cudaStream_t)stream);
+}
+
+int read_conv_plan_impl(const read_conv_plan *p) { return p ? p->impl : 0; }
+
+void read_conv_plan_destroy(read_conv_plan *p)
+{
+    if (!p) return;
+    if (p->tc) tc_plan_destroy(p->tc);
+    delete p;
+}
+
+}  // extern "C"

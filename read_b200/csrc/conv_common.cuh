@@ -1,0 +1,39 @@
+// Shared pieces of the gated-conv kernels.
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+// BasicConv tail (READ/models/unet.py:44-51): BN( A(f) * sigmoid(m) ), eval-mode BN folded to scale/shift.
+// f, m already include their biases.
+__device__ __forceinline__ float gated_epilogue(float f, float m, int elu, float scale, float shift)
+{
+    const float a = (elu && f <= 0.f) ? expm1f(f) : f;   // nn.ELU(alpha=1)
+    const float s = 1.f / (1.f + expf(-m));              // nn.Sigmoid
+    return fmaf(a * s, scale, shift);
+}
+
+// Fast variant for the bf16 tensor-core path: 1 MUFU for ELU (ex2), 1 MUFU for the gate (tanh).
+__device__ __forceinline__ float gated_epilogue_fast(float f, float m, int elu, float scale, float shift)
+{
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f * 1.4426950408889634f));
+    const float a = (elu && f <= 0.f) ? (e - 1.f) : f;
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * m));
+    const float s = fmaf(0.5f, th, 0.5f);                // sigmoid(m) = 0.5*tanh(m/2)+0.5
+    return fmaf(a * s, scale, shift);
+}
+
+int generic_npad(int Cout);
+int generic_kpad(int K);
+int launch_generic(const read_conv_desc &d, cudaStream_t st);
+
+// tcgen05 path (conv_tc.cu)
+struct TcPlan;
+bool tc_supported(const read_conv_desc &d);
+int tc_plan_create(const read_conv_desc &d, TcPlan **out);
+int tc_plan_launch(const TcPlan *p, cudaStream_t st);
+void tc_plan_destroy(TcPlan *p);
+
+}  // namespace rb

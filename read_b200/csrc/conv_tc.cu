@@ -1,0 +1,538 @@
+// Gated convolution as an implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// One kernel computes  y = BN( A(conv_f(x)+b_f) * sigmoid(conv_m(x)+b_m) ) [+ residual]  (BasicConv,
+// READ/models/unet.py:22-53) for stride-1 k x k convolutions over NHWC bf16 activations:
+//
+//   GEMM view   D[M = 128 output pixels (8 rows x 16 cols of one image), N = f|m channels] +=
+//               A[M, K = one filter tap x CIN_BLK input channels] * B[N, K]
+//   A operand   TMA 4-D tile load {c, x, y, b} of the input at the tap-shifted position; rows/cols
+//               outside the image are ZERO-FILLED by the TMA unit == the conv's zero padding
+//               (unet.py:29,36: padding=int((k-1)/2), zeros).  Lands in smem as 128 pixel rows of
+//               CIN_BLK bf16 (64 or 128 bytes) with the matching 64B/128B swizzle: exactly the canonical
+//               K-major UMMA operand layout, so no im2col is ever materialised.
+//   B operand   packed weights [tap][kchunk][n][CIN_BLK] bf16, conv_f and conv_m side by side in N so
+//               ONE accumulator tile holds both gates of the same output channels.
+//   D           fp32 in TMEM, double buffered (2 x up to 256 columns): the epilogue of tile i overlaps the
+//               MMAs of tile i+1.
+//   epilogue    tcgen05.ld -> bias, ELU, sigmoid gate, BN affine, residual add, bf16 pack -> global
+//               (optionally a second output y*z for the following FAM, unet.py:115).
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
+// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quadrant = warp%4).
+#include "common.cuh"
+#include "conv_common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <new>
+
+namespace rb {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_TW = 16, TC_TH = 8;          // 128-pixel M tile
+constexpr int TC_MAX_STAGES = 8;
+constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_TMEM_COLS = 512;
+
+struct TcArgs {
+    int B, H, W, Cin, Cout;
+    int ksize, pad;
+    int cin_blk, kchunks;
+    int n_tile, n_tiles;
+    int tiles_x, tiles_y;
+    int stages;
+    uint32_t a_bytes, b_bytes;
+    int elu;
+    const float *bias_f, *bias_m, *scale, *shift;
+    const __nv_bfloat16 *residual;
+    __nv_bfloat16 *out;
+    __nv_bfloat16 *out2;
+    const __nv_bfloat16 *out2_mul;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "LAB_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint32_t bar, uint32_t dst, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 | [46,48) version=1 |
+//   [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
+{
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u));
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ TcArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
+
+    const uint32_t stage_bytes = a.a_bytes + a.b_bytes;
+    const uint32_t ring_bytes = stage_bytes * (uint32_t)a.stages;
+    // barriers + tmem pointer live after the ring
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + ring_bytes);
+    const uint32_t full0 = s_u32(bars);                       // [TC_MAX_STAGES]
+    const uint32_t empty0 = full0 + 8 * TC_MAX_STAGES;        // [TC_MAX_STAGES]
+    const uint32_t tfull0 = empty0 + 8 * TC_MAX_STAGES;       // [2]
+    const uint32_t tempty0 = tfull0 + 16;                     // [2]
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 4);
+    float *s_par = reinterpret_cast<float *>(bars + 2 * TC_MAX_STAGES + 6);   // 4 x Cout floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < a.Cout; i += TC_THREADS) {
+        s_par[i] = a.bias_f[i];
+        s_par[a.Cout + i] = a.bias_m[i];
+        s_par[2 * a.Cout + i] = a.scale[i];
+        s_par[3 * a.Cout + i] = a.shift[i];
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int m_tiles = a.tiles_x * a.tiles_y * a.B;
+    const long long total_tiles = (long long)m_tiles * a.n_tiles;
+    const int ntaps = a.ksize * a.ksize;
+    const int ksteps = ntaps * a.kchunks;
+    const int n_total = a.n_tile * a.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = (int)(t % a.n_tiles);
+            int mt = (int)(t / a.n_tiles);
+            const int tx = mt % a.tiles_x;
+            mt /= a.tiles_x;
+            const int ty = mt % a.tiles_y;
+            const int b = mt / a.tiles_y;
+            const int x0 = tx * TC_TW, y0 = ty * TC_TH;
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
+                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_arrive_expect_tx(fb, stage_bytes);
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    tma_load_4d(&tmA, fb, sa, kc * a.cin_blk, x0 + kx - a.pad, y0 + ky - a.pad, b);
+                    tma_load_2d(&tmB, fb, sa + a.a_bytes, 0, (tap * a.kchunks + kc) * n_total + nt * a.n_tile);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t layout_type = (a.cin_blk == 64) ? 2u : 4u;
+        const uint32_t sbo = 8u * (uint32_t)a.cin_blk * 2u;   // 8 rows of the swizzle atom
+        uint32_t it = 0, tile_it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+            mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256u;
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * stage_bytes;
+                const uint64_t adesc = make_kmajor_desc(sa, sbo, layout_type);
+                const uint64_t bdesc = make_kmajor_desc(sa + a.a_bytes, sbo, layout_type);
+                const int kk_n = a.cin_blk / 16;
+                for (int kk = 0; kk < kk_n; ++kk) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+                    umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(tfull0 + 8 * acc);
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;             // accumulator row == pixel within the tile
+        const int py = r / TC_TW, px = r % TC_TW;
+        const int half = a.n_tile >> 1;
+        uint32_t tile_it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const int nt = (int)(t % a.n_tiles);
+            int mt = (int)(t / a.n_tiles);
+            const int tx = mt % a.tiles_x;
+            mt /= a.tiles_x;
+            const int ty = mt % a.tiles_y;
+            const int b = mt / a.tiles_y;
+            const int x = tx * TC_TW + px, y = ty * TC_TH + py;
+            const bool inside = (x < a.W) && (y < a.H);
+            const long long pix = ((long long)b * a.H + y) * a.W + x;
+            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tcgen05_fence_after();
+            const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < half; c0 += 16) {
+                uint32_t rf[16], rm[16];
+                tmem_ld16(trow + (uint32_t)c0, rf);
+                tmem_ld16(trow + (uint32_t)(half + c0), rm);
+                tmem_ld_wait();
+                const int co = nt * half + c0;
+                float yv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    yv[j] = gated_epilogue_fast(__uint_as_float(rf[j]) + s_par[co + j],
+                                                __uint_as_float(rm[j]) + s_par[a.Cout + co + j], a.elu,
+                                                s_par[2 * a.Cout + co + j], s_par[3 * a.Cout + co + j]);
+                }
+                if (inside) {
+                    const long long o = pix * a.Cout + co;
+                    if (a.residual) {
+                        const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 f = unpack_bf16x2(rr[j]);
+                            yv[2 * j] += f.x;
+                            yv[2 * j + 1] += f.y;
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                    uint4 *op = reinterpret_cast<uint4 *>(a.out + o);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (a.out2) {
+                        const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        const uint4 m1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
+                        const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                        uint32_t p2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
+                            const float2 mv = unpack_bf16x2(mm[j]);
+                            p2[j] = pack_bf16x2(ys.x * mv.x, ys.y * mv.y);
+                        }
+                        uint4 *o2 = reinterpret_cast<uint4 *>(a.out2 + o);
+                        o2[0] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        o2[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ weight packing
+// out[((tap*kchunks + kc) * n_total + n) * cin_blk + kk],  n -> (tile nt, f|m half, channel)
+__global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__restrict__ wm, int Cout, int Cin, int k,
+                               int cin_blk, int n_tile, __nv_bfloat16 *__restrict__ out)
+{
+    const int kchunks = Cin / cin_blk;
+    const int n_total = 2 * Cout;
+    const int half = n_tile / 2;
+    const long long total = (long long)k * k * kchunks * n_total * cin_blk;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % cin_blk);
+        long long r = i / cin_blk;
+        const int n = (int)(r % n_total);
+        r /= n_total;
+        const int kc = (int)(r % kchunks);
+        const int tap = (int)(r / kchunks);
+        const int nt = n / n_tile, rr = n % n_tile;
+        const bool is_m = rr >= half;
+        const int co = nt * half + (rr % half);
+        const int c = kc * cin_blk + kk;
+        const int ky = tap / k, kx = tap % k;
+        const float *w = is_m ? wm : wf;
+        out[i] = __float2bfloat16_rn(w[(((long long)co * Cin + c) * k + ky) * k + kx]);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct TcGeom {
+    int cin_blk, kchunks, n_tile, n_tiles;
+};
+static bool tc_geom(int Cin, int Cout, TcGeom *g)
+{
+    int cin_blk;
+    if (Cin % 64 == 0) cin_blk = 64;
+    else if (Cin % 32 == 0) cin_blk = 32;
+    else return false;
+    if (Cout % 16 != 0) return false;
+    const int n_total = 2 * Cout;
+    const int n_tile = n_total <= 256 ? n_total : 256;
+    if (n_total % n_tile != 0) return false;
+    if ((n_tile / 2) % 16 != 0) return false;
+    if (g) *g = TcGeom{cin_blk, Cin / cin_blk, n_tile, n_total / n_tile};
+    return true;
+}
+
+bool tc_supported(const read_conv_desc &d)
+{
+    if (d.act_dtype != READ_ACT_BF16) return false;
+    if (d.n_src != 1 || d.src[0].mode != READ_SRC_IDENTITY || d.mul != nullptr) return false;
+    if (d.stride != 1 || !(d.k == 3 || d.k == 1)) return false;
+    if (d.pad != (d.k - 1) / 2) return false;
+    if (d.out_mode != READ_OUT_NHWC) return false;
+    if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+    return tc_geom(d.Cin, d.Cout, nullptr);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+struct TcPlan {
+    CUtensorMap tmA, tmB;
+    TcArgs args;
+    size_t smem_bytes;
+};
+
+int tc_plan_create(const read_conv_desc &d, TcPlan **out)
+{
+    TcGeom g;
+    if (!tc_supported(d) || !tc_geom(d.Cin, d.Cout, &g)) {
+        set_error("tcgen05 conv: unsupported layer");
+        return READ_ERR_UNSUPPORTED;
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("tcgen05 conv: cuTensorMapEncodeTiled not available from the driver");
+        return READ_ERR_CUDA;
+    }
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.w_tc) & 127) == 0, "tcgen05 conv: packed weights must be 128B aligned");
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "tcgen05 conv: output must be 16B aligned");
+    RB_CHECK_ARG(d.residual == nullptr || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, "tcgen05 conv: residual must be 16B aligned");
+    TcPlan *p = new (std::nothrow) TcPlan{};
+    RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
+
+    const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    {   // activations: dims {C, W, H, B}
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, TC_TW, TC_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.src[0].ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tcgen05 conv: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+            delete p;
+            return READ_ERR_CUDA;
+        }
+    }
+    {   // weights: dims {cin_blk, ksteps * n_total}
+        const cuuint64_t rows = (cuuint64_t)d.k * d.k * g.kchunks * 2 * d.Cout;
+        cuuint64_t dims[2] = {(cuuint64_t)g.cin_blk, rows};
+        cuuint64_t strides[1] = {(cuuint64_t)g.cin_blk * 2};
+        cuuint32_t box[2] = {(cuuint32_t)g.cin_blk, (cuuint32_t)g.n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.w_tc), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tcgen05 conv: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+            delete p;
+            return READ_ERR_CUDA;
+        }
+    }
+    TcArgs &a = p->args;
+    a.B = d.B; a.H = d.Hout; a.W = d.Wout; a.Cin = d.Cin; a.Cout = d.Cout;
+    a.ksize = d.k; a.pad = d.pad;
+    a.cin_blk = g.cin_blk; a.kchunks = g.kchunks; a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
+    a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
+    a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
+    a.a_bytes = 128u * g.cin_blk * 2u;
+    a.b_bytes = (uint32_t)g.n_tile * g.cin_blk * 2u;
+    int stages = (int)(TC_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    a.stages = stages;
+    a.elu = d.elu;
+    a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
+    a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
+    a.out = static_cast<__nv_bfloat16 *>(d.out);
+    a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
+    a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
+    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * TC_MAX_STAGES + 6) + 16 * (size_t)d.Cout + 64;
+    *out = p;
+    return READ_OK;
+}
+
+int tc_plan_launch(const TcPlan *p, cudaStream_t st)
+{
+    const TcArgs &a = p->args;
+    const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
+    if (total_tiles == 0) return READ_OK;
+    RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    long long grid = num_sms();
+    if (grid > total_tiles) grid = total_tiles;
+    gated_conv_tc_kernel<<<(unsigned)grid, TC_THREADS, p->smem_bytes, st>>>(p->tmA, p->tmB, a);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+void tc_plan_destroy(TcPlan *p) { delete p; }
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+int64_t read_tc_weight_elems(int Cout, int Cin, int k)
+{
+    if (!tc_geom(Cin, Cout, nullptr)) return -1;
+    return (int64_t)k * k * Cin * 2 * Cout;
+}
+
+int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream)
+{
+    TcGeom g;
+    RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc: null pointer");
+    RB_CHECK_ARG(tc_geom(Cin, Cout, &g), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
+    const long long total = (long long)k * k * Cin * 2 * Cout;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 65535) blocks = 65535;
+    pack_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(wf, wm, Cout, Cin, k, g.cin_blk, g.n_tile,
+                                                                      (__nv_bfloat16 *)out_bf16);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Refinement-net engine: lowers UNet.forward (READ/models/unet.py:202-285) to a static list of fused
+gated-conv launches over NHWC activations, optionally replayed as one CUDA graph.
+
+Every BasicConv (unet.py:22-53) is ONE kernel: conv_f + conv_m + bias + ELU + sigmoid gate + eval-BN affine,
+with the graph glue folded in: torch.cat -> virtual concat, F.interpolate / nn.Upsample -> resampling operand
+loader, ResBlock / FAM skip -> residual add in the epilogue, FAM product -> second epilogue output.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+_MODE = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_UP, "bil4": L.SRC_BILINEAR_UP4}
+
+
+class _Layer:
+    __slots__ = ("name", "plan", "impl", "keep", "flops")
+
+
+class UNetEngine:
+    """Static-shape executor.  ``precision``: 'bf16' (tcgen05 tensor cores where supported) or 'fp32'
+    (CUDA-core parity mode).  ``conv_impl``: 'auto' | 'generic' (force the CUDA-core kernel everywhere)."""
+
+    def __init__(self, state_dict, B, H, W, device, precision="bf16", conv_impl="auto", use_graph=True,
+                 base=32, num_res=4):
+        L.require_device(torch.device(device).index)
+        if H % 16 or W % 16:
+            # READ/gl/nn.py:107-109 asserts the same: the 4x4/s2 + x4-bilinear decoder needs it
+            raise RuntimeError(f"set width {16 * (W // 16)} / height {16 * (H // 16)}: sizes must be multiples of 16")
+        assert precision in ("bf16", "fp32") and conv_impl in ("auto", "generic")
+        self.lib = L.load()
+        self.B, self.H, self.W = B, H, W
+        self.device = torch.device(device)
+        self.bf16 = precision == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32
+        self.act_code = L.ACT_BF16 if self.bf16 else L.ACT_F32
+        self.conv_impl = conv_impl
+        self.base, self.num_res = base, num_res
+        self.sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
+                   if v.dtype.is_floating_point}
+        self.layers = []
+        self._keep = []          # tensors the plans point into
+        self.use_graph = use_graph
+        self.graph = None
+        with torch.cuda.device(self.device):
+            self._build()
+
+    # ------------------------------------------------------------------ weights
+    def _params(self, prefix, cin, cout, k):
+        sd = self.sd
+        wf, wm = sd[prefix + ".block.conv_f.weight"], sd[prefix + ".block.conv_m.weight"]
+        assert tuple(wf.shape) == (cout, cin, k, k), (prefix, tuple(wf.shape), (cout, cin, k, k))
+        bf, bm = sd[prefix + ".block.conv_f.bias"], sd[prefix + ".block.conv_m.bias"]
+        n = prefix + ".block.norm."
+        scale = (sd[n + "weight"] / torch.sqrt(sd[n + "running_var"] + 1e-5)).contiguous()   # eval BN, eps 1e-5
+        shift = (sd[n + "bias"] - sd[n + "running_mean"] * scale).contiguous()
+        return wf, wm, bf, bm, scale, shift
+
+    # ------------------------------------------------------------------ one fused gated conv
+    def _conv(self, prefix, srcs, cout, k, stride, elu, residual=None, out2_mul=None, final=False):
+        """srcs: list of (tensor [B,h,w,c], mode, factor).  Returns out (and out2 if out2_mul)."""
+        lib = self.lib
+        d = L.ReadConvDesc()
+        d.act_dtype = self.act_code
+        d.n_src = len(srcs)
+        cin = 0
+        hin = win = None
+        for i, (t, mode, f) in enumerate(srcs):
+            _, h, w, c = t.shape
+            d.src[i].ptr = t.data_ptr()
+            d.src[i].C, d.src[i].H, d.src[i].W = c, h, w
+            d.src[i].mode, d.src[i].factor = _MODE[mode], f
+            eh, ew = {"id": (h, w), "down": (h // f, w // f), "up": (h * f, w * f), "bil4": (h * 4, w * 4)}[mode]
+            if hin is None:
+                hin, win = eh, ew
+            assert (eh, ew) == (hin, win), (prefix, eh, ew, hin, win)
+            cin += c
+        pad = int((k - 1) / 2)                                   # unet.py:29
+        hout = (hin + 2 * pad - k) // stride + 1
+        wout = (win + 2 * pad - k) // stride + 1
+        wf, wm, bf, bm, scale, shift = self._params(prefix, cin, cout, k)
+        d.B, d.Hin, d.Win, d.Cin = self.B, hin, win, cin
+        d.Hout, d.Wout, d.Cout = hout, wout, cout
+        d.k, d.stride, d.pad, d.elu = k, stride, pad, int(elu)
+        d.bias_f, d.bias_m, d.bn_scale, d.bn_shift = bf.data_ptr(), bm.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        if final:
+            out = torch.empty((self.B, cout, hout, wout), dtype=torch.float32, device=self.device)
+            d.out_mode = L.OUT_NCHW_F32
+        else:
+            out = torch.empty((self.B, hout, wout, cout), dtype=self.adt, device=self.device)
+            d.out_mode = L.OUT_NHWC
+        d.out = out.data_ptr()
+        out2 = None
+        if residual is not None:
+            assert tuple(residual.shape) == (self.B, hout, wout, cout)
+            d.residual = residual.data_ptr()
+        if out2_mul is not None:
+            assert tuple(out2_mul.shape) == (self.B, hout, wout, cout)
+            out2 = torch.empty_like(out)
+            d.out2, d.out2_mul = out2.data_ptr(), out2_mul.data_ptr()
+        keep = [wf, wm, bf, bm, scale, shift, out, out2, residual, out2_mul] + [s[0] for s in srcs]
+
+        use_tc = False
+        if self.bf16 and self.conv_impl == "auto":
+            d.impl = L.CONV_TCGEN05
+            use_tc = bool(lib.read_conv_tc_supported(ctypes.byref(d)))
+        stream = L.stream_ptr()
+        if use_tc:
+            n = lib.read_tc_weight_elems(cout, cin, k)
+            wtc = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            L.check(lib.read_pack_weights_tc(wf.data_ptr(), wm.data_ptr(), cout, cin, k, wtc.data_ptr(), stream))
+            d.w_tc = wtc.data_ptr()
+            d.impl = L.CONV_TCGEN05
+            keep.append(wtc)
+        else:
+            npad = lib.read_generic_npad(cout)
+            kpad = ((k * k * cin + 15) // 16) * 16
+            wg = torch.empty(kpad * npad, dtype=torch.float32, device=self.device)
+            L.check(lib.read_pack_weights_generic(wf.data_ptr(), wm.data_ptr(), cout, cin, k, wg.data_ptr(), stream))
+            d.w_generic = wg.data_ptr()
+            d.impl = L.CONV_GENERIC
+            keep.append(wg)
+        plan = L.c_vp()
+        L.check(lib.read_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
+        ly = _Layer()
+        ly.name, ly.plan, ly.impl, ly.keep = prefix, plan, lib.read_conv_plan_impl(plan), keep
+        ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
+        self.layers.append(ly)
+        return (out, out2) if out2_mul is not None else out
+
+    # ------------------------------------------------------------------ blocks (unet.py:11-117)
+    def _res(self, prefix, x, c):
+        t = self._conv(prefix + ".main.0", [(x, "id", 1)], c, 3, 1, True)
+        return self._conv(prefix + ".main.1", [(t, "id", 1)], c, 3, 1, False, residual=x)
+
+    def _block(self, prefix, x, c):
+        for i in range(self.num_res):
+            x = self._res(f"{prefix}.layers.{i}", x, c)
+        return x
+
+    def _scm(self, prefix, x, c):
+        t = self._conv(prefix + ".main.0", [(x, "id", 1)], c // 4, 3, 1, True)
+        t = self._conv(prefix + ".main.1", [(t, "id", 1)], c // 2, 1, 1, True)
+        t = self._conv(prefix + ".main.2", [(t, "id", 1)], c // 2, 3, 1, True)
+        t = self._conv(prefix + ".main.3", [(t, "id", 1)], c - 8, 1, 1, True)
+        return self._conv(prefix + ".conv", [(x, "id", 1), (t, "id", 1)], c, 1, 1, False)   # cat[x, main(x)]
+
+    def _down_fam(self, fe, fam, x, z_scm, c):
+        """feat_extract[fe] (3x3 s2, ELU) followed by FAM: z + merge(z * z_scm)  (unet.py:225-234)."""
+        z, zz = self._conv(f"feat_extract.{fe}", [(x, "id", 1)], c, 3, 2, True, out2_mul=z_scm)
+        return self._conv(f"{fam}.merge", [(zz, "id", 1)], c, 3, 1, False, residual=z)
+
+    def _aff(self, idx, srcs, c):
+        a = self._conv(f"AFFs.{idx}.conv.0", srcs, c, 1, 1, True)
+        return self._conv(f"AFFs.{idx}.conv.1", [(a, "id", 1)], c, 3, 1, False)
+
+    def _build(self):
+        B, H, W, c = self.B, self.H, self.W, self.base
+        dev, adt = self.device, self.adt
+        self.inputs = [torch.zeros((B, H >> l, W >> l, 8), dtype=adt, device=dev) for l in range(4)]
+        x, x2, x4, x8 = self.inputs
+        z2 = self._scm("SCM2", x2, 2 * c)
+        z4 = self._scm("SCM1", x4, 4 * c)
+        z8 = self._scm("SCM0", x8, 8 * c)
+        x_ = self._conv("feat_extract.0", [(x, "id", 1)], c, 3, 1, True)
+        res1 = self._block("Encoder.0", x_, c)
+        z = self._down_fam(1, "FAM2", res1, z2, 2 * c)
+        res2 = self._block("Encoder.1", z, 2 * c)
+        z = self._down_fam(2, "FAM1", res2, z4, 4 * c)
+        res3 = self._block("Encoder.2", z, 4 * c)
+        z = self._down_fam(6, "FAM0", res3, z8, 8 * c)
+        z = self._block("Encoder.3", z, 8 * c)
+        # AFFs consume the pre-AFF res1..3 and the Encoder[3] output (unet.py:239-254)
+        r1 = self._aff(0, [(res1, "id", 1), (res2, "up", 2), (res3, "up", 4), (z, "up", 8)], c)
+        r2 = self._aff(1, [(res1, "down", 2), (res2, "id", 1), (res3, "up", 2), (z, "up", 4)], 2 * c)
+        r3 = self._aff(2, [(res1, "down", 4), (res2, "down", 2), (res3, "id", 1), (z, "up", 2)], 4 * c)
+        z = self._block("Decoder.0", z, 8 * c)
+        t = self._conv("feat_extract.7", [(z, "id", 1)], 4 * c, 4, 2, True)
+        z = self._conv("Convs.0", [(t, "bil4", 4), (r3, "id", 1)], 4 * c, 1, 1, True)
+        z = self._block("Decoder.1", z, 4 * c)
+        t = self._conv("feat_extract.3", [(z, "id", 1)], 2 * c, 4, 2, True)
+        z = self._conv("Convs.1", [(t, "bil4", 4), (r2, "id", 1)], 2 * c, 1, 1, True)
+        z = self._block("Decoder.2", z, 2 * c)
+        t = self._conv("feat_extract.4", [(z, "id", 1)], c, 4, 2, True)
+        z = self._conv("Convs.2", [(t, "bil4", 4), (r1, "id", 1)], c, 1, 1, True)
+        z = self._block("Decoder.3", z, c)
+        self.output = self._conv("feat_extract.5", [(z, "id", 1)], 3, 3, 1, False, final=True)
+        self.flops = sum(l.flops for l in self.layers)
+        torch.cuda.current_stream().synchronize()   # weight packing done before any capture
+
+    # ------------------------------------------------------------------ execution
+    def _launch_all(self):
+        lib, stream = self.lib, L.stream_ptr()
+        for ly in self.layers:
+            L.check(lib.read_conv_plan_launch(ly.plan, stream))
+
+    def run(self):
+        """Run the net on whatever is in ``self.inputs``; result in ``self.output`` ([B,3,H,W] f32)."""
+        if not self.use_graph:
+            self._launch_all()
+            return self.output
+        if self.graph is None:
+            self._launch_all()                               # warm-up outside capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_all()
+            self.graph = g
+        self.graph.replay()
+        return self.output
+
+    def n_launches(self):
+        return len(self.layers)
+
+    def impl_histogram(self):
+        h = {"tcgen05": 0, "generic": 0}
+        for ly in self.layers:
+            h["tcgen05" if ly.impl == L.CONV_TCGEN05 else "generic"] += 1
+        return h
+
+    def set_inputs_nchw(self, feats):
+        """feats: 4 tensors [B,8,h_l,w_l] f32 cuda -> engine input buffers (NHWC act dtype)."""
+        lib, stream = self.lib, L.stream_ptr()
+        for l in range(4):
+            f = feats[l]
+            if not (f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()):
+                f = f.to(self.device, torch.float32).contiguous()
+            assert tuple(f.shape) == (self.B, 8, self.H >> l, self.W >> l), (tuple(f.shape), l)
+            L.check(lib.read_nchw_f32_to_nhwc(f.data_ptr(), self.B, 8, self.H >> l, self.W >> l, self.act_code,
+                                              self.inputs[l].data_ptr(), stream))
+
+    def __del__(self):
+        try:
+            for ly in self.layers:
+                self.lib.read_conv_plan_destroy(ly.plan)
+        except Exception:
+            pass
