@@ -129,7 +129,7 @@ int read_gather_backward(const float *grad_out, const float *ids, int B, int D, 
 enum { READ_ACT_F32 = 0, READ_ACT_BF16 = 1 };
 enum { READ_SRC_IDENTITY = 0, READ_SRC_NEAREST_DOWN = 1, READ_SRC_NEAREST_UP = 2, READ_SRC_BILINEAR_UP4 = 3 };
 enum { READ_OUT_NHWC = 0, READ_OUT_NCHW_F32 = 1 };
-enum { READ_CONV_AUTO = 0, READ_CONV_GENERIC = 1, READ_CONV_TCGEN05 = 2 };
+enum { READ_CONV_AUTO = 0, READ_CONV_GENERIC = 1, READ_CONV_TCGEN05 = 2, READ_CONV_TCGEN05_GATHER = 3 };
 
 typedef struct read_src {
     const void *ptr;   /* [B, H, W, C] NHWC, activation dtype */
@@ -156,7 +156,7 @@ typedef struct read_conv_desc {
     int32_t out_mode;               /* READ_OUT_* */
     void *out2;                     /* optional second NHWC output: out2 = y * out2_mul (feeds a FAM) */
     const void *out2_mul;
-    int32_t impl;                   /* READ_CONV_* request */
+    int32_t impl;                   /* READ_CONV_* : which kernel (must match the packed weights) */
 } read_conv_desc;
 
 typedef struct read_conv_plan read_conv_plan;
@@ -169,13 +169,18 @@ int read_pack_weights_generic(const float *wf, const float *wm, int Cout, int Ci
 int64_t read_tc_weight_elems(int Cout, int Cin, int k);
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16,
                          void *stream);
-/* 1 if the tcgen05 kernel supports this layer (shape/dtype), else 0 (-> generic CUDA-core kernel). */
+/* 1 if the tcgen05 TMA kernel (stride-1, single source) supports this layer, else 0. */
 int read_conv_tc_supported(const read_conv_desc *d);
+/* Same for the tcgen05 kernel with a gathered A operand (any stride / concat / resampling, bf16 activations);
+ * it has its own weight packing. */
+int read_conv_tcg_supported(const read_conv_desc *d);
+int64_t read_tcg_weight_elems(int Cout, int Cin, int k);
+int read_pack_weights_tcg(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream);
 
 /* Plan = validated descriptor + chosen kernel + TMA tensor maps.  Host-side only, no device work. */
 int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out);
 int read_conv_plan_launch(const read_conv_plan *p, void *stream);
-int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC or READ_CONV_TCGEN05 */
+int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC / _TCGEN05 / _TCGEN05_GATHER */
 void read_conv_plan_destroy(read_conv_plan *p);
 
 /* Layout converters at the net boundary. */

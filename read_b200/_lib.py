@@ -20,7 +20,7 @@ TEXACT = {"none": 0, "sigmoid": 1, "tanh": 2}
 ACT_F32, ACT_BF16 = 0, 1
 SRC_IDENTITY, SRC_NEAREST_DOWN, SRC_NEAREST_UP, SRC_BILINEAR_UP4 = 0, 1, 2, 3
 OUT_NHWC, OUT_NCHW_F32 = 0, 1
-CONV_AUTO, CONV_GENERIC, CONV_TCGEN05 = 0, 1, 2
+CONV_AUTO, CONV_GENERIC, CONV_TCGEN05, CONV_TCGEN05_GATHER = 0, 1, 2, 3
 
 
 class ReadSrc(ctypes.Structure):
@@ -66,6 +66,9 @@ _SIGS = {
     "read_tc_weight_elems": (c_i64, [c_int, c_int, c_int]),
     "read_pack_weights_tc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_conv_tc_supported": (c_int, [ctypes.POINTER(ReadConvDesc)]),
+    "read_conv_tcg_supported": (c_int, [ctypes.POINTER(ReadConvDesc)]),
+    "read_tcg_weight_elems": (c_i64, [c_int, c_int, c_int]),
+    "read_pack_weights_tcg": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_conv_plan_create": (c_int, [ctypes.POINTER(ReadConvDesc), ctypes.POINTER(c_vp)]),
     "read_conv_plan_launch": (c_int, [c_vp, c_vp]),
     "read_conv_plan_impl": (c_int, [c_vp]),

@@ -41,6 +41,7 @@ struct read_conv_plan {
     read_conv_desc d;
     int impl;
     TcPlan *tc;
+    TcgPlan *tcg;
 };
 
 static int validate_conv(const read_conv_desc &d)
@@ -102,24 +103,45 @@ int read_conv_tc_supported(const read_conv_desc *d)
     return tc_supported(*d) ? 1 : 0;
 }
 
+int read_conv_tcg_supported(const read_conv_desc *d)
+{
+    if (!d) return 0;
+    return tcg_supported(*d) ? 1 : 0;
+}
+
+int64_t read_tcg_weight_elems(int Cout, int Cin, int k) { return tcg_weight_elems(Cout, Cin, k); }
+
+int read_pack_weights_tcg(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream)
+{
+    RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc_gather: null pointer");
+    return tcg_pack(wf, wm, Cout, Cin, k, out_bf16, (cudaStream_t)stream);
+}
+
 int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out)
 {
     RB_CHECK_ARG(d && out, "conv plan: null argument");
     int rc = validate_conv(*d);
     if (rc) return rc;
     int impl = d->impl;
-    if (impl == READ_CONV_AUTO) impl = (d->w_tc && tc_supported(*d)) ? READ_CONV_TCGEN05 : READ_CONV_GENERIC;
+    RB_CHECK_ARG(impl != READ_CONV_AUTO, "conv plan: choose impl explicitly (the weight packing differs per kernel)");
     if (impl == READ_CONV_TCGEN05) {
         RB_CHECK_ARG(d->w_tc != nullptr, "conv plan: tcgen05 requested without packed bf16 weights");
-        if (!tc_supported(*d)) { set_error("conv plan: layer shape not supported by the tcgen05 kernel"); return READ_ERR_UNSUPPORTED; }
+        if (!tc_supported(*d)) { set_error("conv plan: layer shape not supported by the tcgen05 TMA kernel"); return READ_ERR_UNSUPPORTED; }
+    } else if (impl == READ_CONV_TCGEN05_GATHER) {
+        RB_CHECK_ARG(d->w_tc != nullptr, "conv plan: tcgen05 requested without packed bf16 weights");
+        if (!tcg_supported(*d)) { set_error("conv plan: layer not supported by the tcgen05 gather kernel"); return READ_ERR_UNSUPPORTED; }
     } else {
+        RB_CHECK_ARG(impl == READ_CONV_GENERIC, "conv plan: unknown impl %d", impl);
         RB_CHECK_ARG(d->w_generic != nullptr, "conv plan: generic kernel needs w_generic");
         RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d->w_generic) & 15) == 0, "conv plan: w_generic must be 16B aligned");
     }
-    read_conv_plan *p = new (std::nothrow) read_conv_plan{*d, impl, nullptr};
+    read_conv_plan *p = new (std::nothrow) read_conv_plan{*d, impl, nullptr, nullptr};
     RB_CHECK_ARG(p != nullptr, "conv plan: out of host memory");
     if (impl == READ_CONV_TCGEN05) {
         rc = tc_plan_create(*d, &p->tc);
+        if (rc) { delete p; return rc; }
+    } else if (impl == READ_CONV_TCGEN05_GATHER) {
+        rc = tcg_plan_create(*d, &p->tcg);
         if (rc) { delete p; return rc; }
     }
     *out = p;
@@ -130,6 +152,7 @@ int read_conv_plan_launch(const read_conv_plan *p, void *stream)
 {
     RB_CHECK_ARG(p != nullptr, "conv plan: null plan");
     if (p->impl == READ_CONV_TCGEN05) return tc_plan_launch(p->tc, (cudaStream_t)stream);
+    if (p->impl == READ_CONV_TCGEN05_GATHER) return tcg_plan_launch(p->tcg, (cudaStream_t)stream);
     return launch_generic(p->d, (cudaStream_t)stream);
 }
 
@@ -139,6 +162,7 @@ void read_conv_plan_destroy(read_conv_plan *p)
 {
     if (!p) return;
     if (p->tc) tc_plan_destroy(p->tc);
+    if (p->tcg) tcg_plan_destroy(p->tcg);
     delete p;
 }
 

@@ -36,4 +36,14 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out);
 int tc_plan_launch(const TcPlan *p, cudaStream_t st);
 void tc_plan_destroy(TcPlan *p);
 
+
+// tcgen05 path with gathered A operand (conv_tc_gather.cu)
+struct TcgPlan;
+bool tcg_supported(const read_conv_desc &d);
+int tcg_plan_create(const read_conv_desc &d, TcgPlan **out);
+int tcg_plan_launch(const TcgPlan *p, cudaStream_t st);
+void tcg_plan_destroy(TcgPlan *p);
+int64_t tcg_weight_elems(int Cout, int Cin, int k);
+int tcg_pack(const float *wf, const float *wm, int Cout, int Cin, int k, void *out, cudaStream_t st);
+
 }  // namespace rb

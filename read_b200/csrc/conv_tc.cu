@@ -21,6 +21,7 @@
 // warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quadrant = warp%4).
 #include "common.cuh"
 #include "conv_common.cuh"
+#include "ptx.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <new>
@@ -48,94 +49,6 @@ struct TcArgs {
     __nv_bfloat16 *out2;
     const __nv_bfloat16 *out2_mul;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LAB_DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "LAB_DONE:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap *tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint32_t bar, uint32_t dst, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 | [46,48) version=1 |
-//   [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 {
@@ -176,8 +89,8 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         s_par[3 * a.Cout + i] = a.shift[i];
     }
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) {
@@ -188,14 +101,9 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, 4);   // one arrival per epilogue warp
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr_smem)),
-                     "r"((uint32_t)TC_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) tmem_alloc(s_u32(tmem_ptr_smem), TC_TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -338,8 +246,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
-                     : "memory");
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
     }
 }
 
@@ -404,7 +311,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled get_encode()
+PFN_encodeTiled get_encode_tiled()
 {
     static PFN_encodeTiled fn = nullptr;
     static std::once_flag once;
@@ -431,7 +338,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         set_error("tcgen05 conv: unsupported layer");
         return READ_ERR_UNSUPPORTED;
     }
-    PFN_encodeTiled enc = get_encode();
+    PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) {
         set_error("tcgen05 conv: cuTensorMapEncodeTiled not available from the driver");
         return READ_ERR_CUDA;

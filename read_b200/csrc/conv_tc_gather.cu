@@ -1,0 +1,532 @@
+// General gated convolution on the tcgen05 tensor cores: implicit GEMM whose A operand is GATHERED by four
+// producer warps (cp.async 16-byte chunks, zero-fill for padding) directly into the 128B-swizzled K-major
+// layout the UMMA descriptor expects.  Covers every BasicConv shape of READ/models/unet.py that the pure-TMA kernel
+// (conv_tc.cu) cannot express as shifted tile loads:
+//   * stride-2 3x3 and 4x4 convolutions (feat_extract[1,2,6], [3,4,7])
+//   * virtual concat of up to 4 sources (SCM / AFF / decoder merges: unet.py:88,105,263,271,279)
+//   * nearest up/down resampling of a source (F.interpolate, unet.py:239-250) and bilinear x4 (nn.Upsample, :200)
+//   * channel counts that are only multiples of 8 (8->32 first conv, 32->3 last conv, SCM 16/56/120/248)
+//   * NCHW fp32 output for the final layer
+//
+// GEMM view: M = 128 output pixels (8 rows x 16 cols), K = (tap, cin) flattened in 8-channel chunks and padded to
+// 64-element blocks, N = conv_f | conv_m channels (<= 256 per tile).  Weights arrive by TMA; accumulators live in
+// TMEM (double buffered); the epilogue is the same fused bias/ELU/sigmoid/BN/residual tail as conv_tc.cu.
+//
+// Warp roles (320 threads, 1 CTA/SM, persistent): warp0 = weight TMA + TMEM alloc, warp1 = MMA issuer,
+// warps2-5 = A gather producers (thread -> fixed tile column and fixed 16-byte K chunk, 8 tile rows),
+// warps6-9 = epilogue.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <new>
+
+namespace rb {
+
+constexpr int G_THREADS = 320;
+constexpr int G_TW = 16, G_TH = 8;
+constexpr int G_MAX_STAGES = 8;
+constexpr uint32_t G_SMEM_BUDGET = 192 * 1024;
+constexpr int G_TMEM_COLS = 512;
+constexpr int G_KBLK = 64;                     // elements per K block (128-byte rows, SWIZZLE_128B)
+constexpr int G_LA = 2;                        // cp.async groups kept in flight behind the newest one
+
+struct GSrc {
+    const __nv_bfloat16 *ptr;
+    int C, H, W, mode, factor, c_begin;
+};
+
+struct GArgs {
+    GSrc src[READ_MAX_SRC];
+    int n_src;
+    int B, Hin, Win, Cin, Hout, Wout, Cout, Cout_pad;
+    int ksize, stride, pad;
+    int K, kblocks;
+    int n_tile, n_tiles;
+    int tiles_x, tiles_y;
+    int stages;
+    uint32_t a_bytes, b_bytes;
+    int elu;
+    const float *bias_f, *bias_m, *scale, *shift;
+    const __nv_bfloat16 *residual;
+    void *out;
+    int out_mode;
+    __nv_bfloat16 *out2;
+    const __nv_bfloat16 *out2_mul;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t g_pack2(float a, float b)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float2 g_unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u)); }
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
+
+    const uint32_t stage_bytes = a.a_bytes + a.b_bytes;
+    const uint32_t ring_bytes = stage_bytes * (uint32_t)a.stages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + ring_bytes);
+    const uint32_t full0 = s_u32(bars);
+    const uint32_t empty0 = full0 + 8 * G_MAX_STAGES;
+    const uint32_t tfull0 = empty0 + 8 * G_MAX_STAGES;
+    const uint32_t tempty0 = tfull0 + 16;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * G_MAX_STAGES + 4);
+    float *s_par = reinterpret_cast<float *>(bars + 2 * G_MAX_STAGES + 6);   // 4 x Cout_pad floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CP = a.Cout_pad;
+    for (int i = threadIdx.x; i < CP; i += G_THREADS) {
+        const bool v = i < a.Cout;
+        s_par[i] = v ? a.bias_f[i] : 0.f;
+        s_par[CP + i] = v ? a.bias_m[i] : 0.f;
+        s_par[2 * CP + i] = v ? a.scale[i] : 0.f;
+        s_par[3 * CP + i] = v ? a.shift[i] : 0.f;
+    }
+    if (warp == 1 && lane == 0) {
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(full0 + 8 * s, 128 + 1);   // 128 gather threads + the weight-TMA thread
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(s_u32(tmem_ptr_smem), G_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int m_tiles = a.tiles_x * a.tiles_y * a.B;
+    const long long total_tiles = (long long)m_tiles * a.n_tiles;
+    const int n_total = a.n_tile * a.n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== weight TMA producer =====================
+            uint32_t it = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = (int)(t % a.n_tiles);
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_arrive_expect_tx(fb, a.b_bytes);
+                    tma_load_2d(&tmB, fb, smem_base + s * stage_bytes + a.a_bytes, 0, kb * n_total + nt * a.n_tile);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t it = 0, tile_it = 0;
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+                const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+                mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint64_t adesc = make_kmajor_desc(sa, 1024u, 2u);
+                    const uint64_t bdesc = make_kmajor_desc(sa + a.a_bytes, 1024u, 2u);
+#pragma unroll
+                    for (int kk = 0; kk < G_KBLK / 16; ++kk)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);
+                }
+                umma_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== A gather producers (128 threads) =====================
+        const int t = threadIdx.x - 64;
+        const int j = t & 7;                // 16-byte chunk inside the 128-byte K row
+        const int px = t >> 3;              // tile column handled by this thread (rows r = px + 16*i, i = tile row)
+        const uint32_t dst_off = (uint32_t)px * 128u + (uint32_t)((j ^ (px & 7)) << 4);
+        uint32_t it = 0;
+        for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+            int mt = (int)(tl / a.n_tiles);
+            const int tx = mt % a.tiles_x;
+            mt /= a.tiles_x;
+            const int ty = mt % a.tiles_y;
+            const int b = mt / a.tiles_y;
+            const int ox = tx * G_TW + px, oy0 = ty * G_TH;
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t dst0 = smem_base + s * stage_bytes + dst_off;
+                const int kel = (kb * 8 + j) * 8;
+                bool kvalid = kel < a.K;
+                int ky = 0, kx = 0, si = 0, cl = 0;
+                if (kvalid) {
+                    const int tap = kel / a.Cin;
+                    const int c = kel - tap * a.Cin;
+                    ky = tap / a.ksize;
+                    kx = tap - ky * a.ksize;
+#pragma unroll
+                    for (int q = 1; q < READ_MAX_SRC; ++q)
+                        if (q < a.n_src && c >= a.src[q].c_begin) si = q;
+                    cl = c - a.src[si].c_begin;
+                }
+                const GSrc &sv = a.src[si];
+                const int ix = ox * a.stride - a.pad + kx;
+                const bool xvalid = kvalid && (ox < a.Wout) && (ix >= 0) && (ix < a.Win);
+                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.H * sv.W * sv.C + cl;
+                if (sv.mode != READ_SRC_BILINEAR_UP4) {
+                    int sx = ix;
+                    if (sv.mode == READ_SRC_NEAREST_DOWN) sx = ix * sv.factor;
+                    else if (sv.mode == READ_SRC_NEAREST_UP) sx = ix / sv.factor;
+                    sx = sx < sv.W ? sx : sv.W - 1;
+                    sx = sx < 0 ? 0 : sx;
+#pragma unroll
+                    for (int i = 0; i < G_TH; ++i) {
+                        const int oy = oy0 + i;
+                        const int iy = oy * a.stride - a.pad + ky;
+                        const bool valid = xvalid && (oy < a.Hout) && (iy >= 0) && (iy < a.Hin);
+                        int sy = iy;
+                        if (sv.mode == READ_SRC_NEAREST_DOWN) sy = iy * sv.factor;
+                        else if (sv.mode == READ_SRC_NEAREST_UP) sy = iy / sv.factor;
+                        sy = sy < sv.H ? sy : sv.H - 1;
+                        sy = sy < 0 ? 0 : sy;
+                        const __nv_bfloat16 *p = sbase + ((long long)sy * sv.W + sx) * sv.C;
+                        cp_async16(dst0 + (uint32_t)i * 2048u, valid ? (const void *)p : (const void *)sv.ptr, valid ? 16u : 0u);
+                    }
+                } else {
+                    // bilinear x4, align_corners=False (torch upsample_bilinear2d): src = max(0.25*(dst+0.5)-0.5, 0)
+                    float fx = 0.25f * ((float)ix + 0.5f) - 0.5f;
+                    fx = fx < 0.f ? 0.f : fx;
+                    const int x0 = (int)fx;
+                    const int xp = (x0 < sv.W - 1) ? 1 : 0;
+                    const float lx = fx - (float)x0, hx = 1.f - lx;
+#pragma unroll 2
+                    for (int i = 0; i < G_TH; ++i) {
+                        const int oy = oy0 + i;
+                        const int iy = oy * a.stride - a.pad + ky;
+                        const bool valid = xvalid && (oy < a.Hout) && (iy >= 0) && (iy < a.Hin);
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (valid) {
+                            float fy = 0.25f * ((float)iy + 0.5f) - 0.5f;
+                            fy = fy < 0.f ? 0.f : fy;
+                            const int y0 = (int)fy;
+                            const int yp = (y0 < sv.H - 1) ? 1 : 0;
+                            const float ly = fy - (float)y0, hy = 1.f - ly;
+                            const __nv_bfloat16 *p = sbase + ((long long)y0 * sv.W + x0) * sv.C;
+                            const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(p));
+                            const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)xp * sv.C));
+                            const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)yp * sv.W * sv.C));
+                            const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(p + ((long long)yp * sv.W + xp) * sv.C));
+                            const uint32_t *a00 = &v00.x, *a01 = &v01.x, *a10 = &v10.x, *a11 = &v11.x;
+                            uint32_t r[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f00 = g_unpack2(a00[e]), f01 = g_unpack2(a01[e]), f10 = g_unpack2(a10[e]), f11 = g_unpack2(a11[e]);
+                                r[e] = g_pack2(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
+                                               hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
+                            }
+                            o = make_uint4(r[0], r[1], r[2], r[3]);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)i * 2048u), "r"(o.x), "r"(o.y),
+                                     "r"(o.z), "r"(o.w)
+                                     : "memory");
+                    }
+                }
+                cp_async_commit();
+                if (it >= (uint32_t)G_LA) {
+                    cp_async_wait<G_LA>();
+                    fence_proxy_async();
+                    mbar_arrive(full0 + 8 * ((it - G_LA) % (uint32_t)a.stages));
+                }
+            }
+        }
+        // drain: publish the last min(it, G_LA) stages
+        cp_async_wait<0>();
+        fence_proxy_async();
+        const uint32_t first = it >= (uint32_t)G_LA ? it - G_LA : 0u;
+        for (uint32_t k = first; k < it; ++k) mbar_arrive(full0 + 8 * (k % (uint32_t)a.stages));
+    } else {
+        // ===================== epilogue (warps 6-9) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int py = r / G_TW, pxl = r % G_TW;
+        const int half = a.n_tile >> 1;
+        uint32_t tile_it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const int nt = (int)(t % a.n_tiles);
+            int mt = (int)(t / a.n_tiles);
+            const int tx = mt % a.tiles_x;
+            mt /= a.tiles_x;
+            const int ty = mt % a.tiles_y;
+            const int b = mt / a.tiles_y;
+            const int x = tx * G_TW + pxl, y = ty * G_TH + py;
+            const bool inside = (x < a.Wout) && (y < a.Hout);
+            const long long pix = ((long long)b * a.Hout + y) * a.Wout + x;
+            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tcgen05_fence_after();
+            const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < half; c0 += 8) {
+                uint32_t rf[8], rm[8];
+                tmem_ld8(trow + (uint32_t)c0, rf);
+                tmem_ld8(trow + (uint32_t)(half + c0), rm);
+                tmem_ld_wait();
+                const int co = nt * half + c0;
+                if (co >= a.Cout) continue;          // padded channels (warp-uniform)
+                float yv[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    yv[jj] = gated_epilogue_fast(__uint_as_float(rf[jj]) + s_par[co + jj], __uint_as_float(rm[jj]) + s_par[CP + co + jj],
+                                                 a.elu, s_par[2 * CP + co + jj], s_par[3 * CP + co + jj]);
+                if (inside) {
+                    if (a.out_mode == READ_OUT_NCHW_F32) {
+                        float *o = static_cast<float *>(a.out);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            if (co + jj < a.Cout) o[(((long long)b * a.Cout + co + jj) * a.Hout + y) * a.Wout + x] = yv[jj];
+                    } else {
+                        const long long o = pix * a.Cout + co;
+                        if (a.residual) {
+                            const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                            const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float2 f = g_unpack2(rr[jj]);
+                                yv[2 * jj] += f.x;
+                                yv[2 * jj + 1] += f.y;
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) pk[jj] = g_pack2(yv[2 * jj], yv[2 * jj + 1]);
+                        *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(a.out) + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (a.out2) {
+                            const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                            const uint32_t mm[4] = {m0.x, m0.y, m0.z, m0.w};
+                            uint32_t p2[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float2 ys = g_unpack2(pk[jj]);
+                                const float2 mv = g_unpack2(mm[jj]);
+                                p2[jj] = g_pack2(ys.x * mv.x, ys.y * mv.y);
+                            }
+                            *reinterpret_cast<uint4 *>(a.out2 + o) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, G_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ weight packing
+// out[((kb * n_total + n) * 64 + kk)],  k = kb*64 + kk = (tap*Cin + c) ; n -> (tile, f|m half, channel); zero padded
+__global__ void pack_tcg_kernel(const float *__restrict__ wf, const float *__restrict__ wm, int Cout, int Cin, int k,
+                                int kblocks, int n_tile, int n_tiles, __nv_bfloat16 *__restrict__ out)
+{
+    const int K = k * k * Cin;
+    const int n_total = n_tile * n_tiles;
+    const int half = n_tile / 2;
+    const long long total = (long long)kblocks * n_total * G_KBLK;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % G_KBLK);
+        long long r = i / G_KBLK;
+        const int n = (int)(r % n_total);
+        const int kb = (int)(r / n_total);
+        const int kel = kb * G_KBLK + kk;
+        const int nt = n / n_tile, rr = n % n_tile;
+        const bool is_m = rr >= half;
+        const int co = nt * half + (rr % half);
+        float v = 0.f;
+        if (kel < K && co < Cout) {
+            const int tap = kel / Cin, c = kel % Cin;
+            const int ky = tap / k, kx = tap % k;
+            const float *w = is_m ? wm : wf;
+            v = w[(((long long)co * Cin + c) * k + ky) * k + kx];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct GGeom {
+    int cout_pad, n_tile, n_tiles, kblocks;
+};
+static bool g_geom(int Cin, int Cout, int k, GGeom *g)
+{
+    if (Cin % 8 != 0 || Cout < 1) return false;
+    int cp, n_tile, n_tiles;
+    if (Cout <= 128) {
+        cp = ((Cout + 7) / 8) * 8;
+        n_tile = 2 * cp;
+        n_tiles = 1;
+    } else {
+        cp = ((Cout + 127) / 128) * 128;
+        n_tile = 256;
+        n_tiles = cp / 128;
+    }
+    if (n_tile % 16 != 0 || n_tile > 256) return false;
+    if (g) *g = GGeom{cp, n_tile, n_tiles, (k * k * Cin + G_KBLK - 1) / G_KBLK};
+    return true;
+}
+
+bool tcg_supported(const read_conv_desc &d)
+{
+    if (d.act_dtype != READ_ACT_BF16 || d.mul != nullptr) return false;
+    if (d.out_mode == READ_OUT_NHWC && d.Cout % 8 != 0) return false;
+    for (int i = 0; i < d.n_src; ++i)
+        if (d.src[i].C % 8 != 0) return false;
+    return g_geom(d.Cin, d.Cout, d.k, nullptr);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+struct TcgPlan {
+    CUtensorMap tmB;
+    GArgs args;
+    size_t smem_bytes;
+};
+
+int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
+{
+    GGeom g;
+    if (!tcg_supported(d) || !g_geom(d.Cin, d.Cout, d.k, &g)) {
+        set_error("tcgen05 gather conv: unsupported layer");
+        return READ_ERR_UNSUPPORTED;
+    }
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        set_error("tcgen05 gather conv: cuTensorMapEncodeTiled not available from the driver");
+        return READ_ERR_CUDA;
+    }
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.w_tc) & 127) == 0, "tcgen05 gather conv: packed weights must be 128B aligned");
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "tcgen05 gather conv: output must be 16B aligned");
+    TcgPlan *p = new (std::nothrow) TcgPlan{};
+    RB_CHECK_ARG(p != nullptr, "tcgen05 gather conv: out of host memory");
+    {
+        const cuuint64_t rows = (cuuint64_t)g.kblocks * g.n_tile * g.n_tiles;
+        cuuint64_t dims[2] = {(cuuint64_t)G_KBLK, rows};
+        cuuint64_t strides[1] = {(cuuint64_t)G_KBLK * 2};
+        cuuint32_t box[2] = {(cuuint32_t)G_KBLK, (cuuint32_t)g.n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.w_tc), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tcgen05 gather conv: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+            delete p;
+            return READ_ERR_CUDA;
+        }
+    }
+    GArgs &a = p->args;
+    int cb = 0;
+    for (int i = 0; i < d.n_src; ++i) {
+        a.src[i] = GSrc{static_cast<const __nv_bfloat16 *>(d.src[i].ptr), d.src[i].C, d.src[i].H, d.src[i].W, d.src[i].mode,
+                        d.src[i].factor, cb};
+        cb += d.src[i].C;
+    }
+    for (int i = d.n_src; i < READ_MAX_SRC; ++i) a.src[i] = a.src[0];
+    a.n_src = d.n_src;
+    a.B = d.B; a.Hin = d.Hin; a.Win = d.Win; a.Cin = d.Cin;
+    a.Hout = d.Hout; a.Wout = d.Wout; a.Cout = d.Cout; a.Cout_pad = g.cout_pad;
+    a.ksize = d.k; a.stride = d.stride; a.pad = d.pad;
+    a.K = d.k * d.k * d.Cin; a.kblocks = g.kblocks;
+    a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
+    a.tiles_x = (d.Wout + G_TW - 1) / G_TW;
+    a.tiles_y = (d.Hout + G_TH - 1) / G_TH;
+    a.a_bytes = 128u * G_KBLK * 2u;
+    a.b_bytes = (uint32_t)g.n_tile * G_KBLK * 2u;
+    int stages = (int)(G_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
+    if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
+    a.stages = stages;
+    a.elu = d.elu;
+    a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
+    a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
+    a.out = d.out; a.out_mode = d.out_mode;
+    a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
+    a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
+    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 64;
+    *out = p;
+    return READ_OK;
+}
+
+int tcg_plan_launch(const TcgPlan *p, cudaStream_t st)
+{
+    const GArgs &a = p->args;
+    const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
+    if (total_tiles == 0) return READ_OK;
+    RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    long long grid = num_sms();
+    if (grid > total_tiles) grid = total_tiles;
+    gated_conv_tc_gather_kernel<<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+void tcg_plan_destroy(TcgPlan *p) { delete p; }
+
+int64_t tcg_weight_elems(int Cout, int Cin, int k)
+{
+    GGeom g;
+    if (!g_geom(Cin, Cout, k, &g)) return -1;
+    return (int64_t)g.kblocks * g.n_tile * g.n_tiles * G_KBLK;
+}
+
+int tcg_pack(const float *wf, const float *wm, int Cout, int Cin, int k, void *out, cudaStream_t st)
+{
+    GGeom g;
+    if (!g_geom(Cin, Cout, k, &g)) {
+        set_error("pack_tc_gather: unsupported channel counts %d -> %d", Cin, Cout);
+        return READ_ERR_INVALID;
+    }
+    const long long total = (long long)g.kblocks * g.n_tile * g.n_tiles * G_KBLK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 65535) blocks = 65535;
+    pack_tcg_kernel<<<(unsigned)blocks, 256, 0, st>>>(wf, wm, Cout, Cin, k, g.kblocks, g.n_tile, g.n_tiles, (__nv_bfloat16 *)out);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+}  // namespace rb

@@ -20,7 +20,8 @@ class _Layer:
 
 class UNetEngine:
     """Static-shape executor.  ``precision``: 'bf16' (tcgen05 tensor cores where supported) or 'fp32'
-    (CUDA-core parity mode).  ``conv_impl``: 'auto' | 'generic' (force the CUDA-core kernel everywhere)."""
+    (CUDA-core parity mode).  ``conv_impl``: 'auto' (tcgen05 everywhere it applies) | 'tma_only' (tcgen05 TMA kernel
+    for the stride-1 layers, CUDA cores for the rest) | 'generic' (CUDA-core kernel everywhere)."""
 
     def __init__(self, state_dict, B, H, W, device, precision="bf16", conv_impl="auto", use_graph=True,
                  base=32, num_res=4):
@@ -28,7 +29,7 @@ class UNetEngine:
         if H % 16 or W % 16:
             # READ/gl/nn.py:107-109 asserts the same: the 4x4/s2 + x4-bilinear decoder needs it
             raise RuntimeError(f"set width {16 * (W // 16)} / height {16 * (H // 16)}: sizes must be multiples of 16")
-        assert precision in ("bf16", "fp32") and conv_impl in ("auto", "generic")
+        assert precision in ("bf16", "fp32") and conv_impl in ("auto", "generic", "tma_only")
         self.lib = L.load()
         self.B, self.H, self.W = B, H, W
         self.device = torch.device(device)
@@ -101,25 +102,29 @@ class UNetEngine:
             d.out2, d.out2_mul = out2.data_ptr(), out2_mul.data_ptr()
         keep = [wf, wm, bf, bm, scale, shift, out, out2, residual, out2_mul] + [s[0] for s in srcs]
 
-        use_tc = False
-        if self.bf16 and self.conv_impl == "auto":
-            d.impl = L.CONV_TCGEN05
-            use_tc = bool(lib.read_conv_tc_supported(ctypes.byref(d)))
+        kind = "generic"
+        if self.bf16 and self.conv_impl != "generic":
+            if lib.read_conv_tc_supported(ctypes.byref(d)):
+                kind = "tma"
+            elif self.conv_impl == "auto" and lib.read_conv_tcg_supported(ctypes.byref(d)):
+                kind = "gather"
         stream = L.stream_ptr()
-        if use_tc:
-            n = lib.read_tc_weight_elems(cout, cin, k)
-            wtc = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+        if kind == "tma":
+            wtc = torch.empty(lib.read_tc_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=self.device)
             L.check(lib.read_pack_weights_tc(wf.data_ptr(), wm.data_ptr(), cout, cin, k, wtc.data_ptr(), stream))
-            d.w_tc = wtc.data_ptr()
-            d.impl = L.CONV_TCGEN05
+            d.w_tc, d.impl = wtc.data_ptr(), L.CONV_TCGEN05
+            keep.append(wtc)
+        elif kind == "gather":
+            wtc = torch.empty(lib.read_tcg_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=self.device)
+            L.check(lib.read_pack_weights_tcg(wf.data_ptr(), wm.data_ptr(), cout, cin, k, wtc.data_ptr(), stream))
+            d.w_tc, d.impl = wtc.data_ptr(), L.CONV_TCGEN05_GATHER
             keep.append(wtc)
         else:
             npad = lib.read_generic_npad(cout)
             kpad = ((k * k * cin + 15) // 16) * 16
             wg = torch.empty(kpad * npad, dtype=torch.float32, device=self.device)
             L.check(lib.read_pack_weights_generic(wf.data_ptr(), wm.data_ptr(), cout, cin, k, wg.data_ptr(), stream))
-            d.w_generic = wg.data_ptr()
-            d.impl = L.CONV_GENERIC
+            d.w_generic, d.impl = wg.data_ptr(), L.CONV_GENERIC
             keep.append(wg)
         plan = L.c_vp()
         L.check(lib.read_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
@@ -214,9 +219,10 @@ class UNetEngine:
         return len(self.layers)
 
     def impl_histogram(self):
-        h = {"tcgen05": 0, "generic": 0}
+        names = {L.CONV_GENERIC: "generic", L.CONV_TCGEN05: "tcgen05", L.CONV_TCGEN05_GATHER: "tcgen05_gather"}
+        h = {"tcgen05": 0, "tcgen05_gather": 0, "generic": 0}
         for ly in self.layers:
-            h["tcgen05" if ly.impl == L.CONV_TCGEN05 else "generic"] += 1
+            h[names[ly.impl]] += 1
         return h
 
     def set_inputs_nchw(self, feats):

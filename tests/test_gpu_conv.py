@@ -1,0 +1,236 @@
+"""-m gpu: fused gated-conv kernels vs a plain PyTorch fp32 reference of the same op (BasicConv, unet.py:22-53)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import dev
+from read_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_gated(x, wf, bf, wm, bm, scale, shift, k, stride, elu, residual=None):
+    p = int((k - 1) / 2)
+    f = F.conv2d(x, wf, bf, stride=stride, padding=p)
+    if elu:
+        f = F.elu(f)
+    y = f * torch.sigmoid(F.conv2d(x, wm, bm, stride=stride, padding=p))
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]
+    return y if residual is None else y + residual
+
+
+def resample(t, mode, f):
+    if mode == "id":
+        return t
+    if mode == "down":
+        return F.interpolate(t, scale_factor=1.0 / f)
+    if mode == "up":
+        return F.interpolate(t, scale_factor=f)
+    return F.interpolate(t, scale_factor=4, mode="bilinear", align_corners=False)
+
+
+def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=False, final=False, mul=False, seed=0):
+    """srcs: list of (C, h, w, mode, factor) describing NCHW fp32 source tensors.  Returns (got, want[, got2, want2])."""
+    lib = L.load()
+    d = dev()
+    g = torch.Generator().manual_seed(seed)
+    adt = torch.bfloat16 if act_bf16 else torch.float32
+    B = 2
+    xs = [torch.rand((B, c, h, w), generator=g) * 2 - 1 for (c, h, w, _, _) in srcs]
+    if act_bf16:
+        xs = [x.to(torch.bfloat16).float() for x in xs]
+    logical = torch.cat([resample(x, m, f) for x, (_, _, _, m, f) in zip(xs, srcs)], 1)
+    cin, hin, win = logical.shape[1:]
+    bound = 1.0 / (cin * k * k) ** 0.5
+    wf = (torch.rand((cout, cin, k, k), generator=g) * 2 - 1) * bound
+    wm = (torch.rand((cout, cin, k, k), generator=g) * 2 - 1) * bound
+    bf = (torch.rand(cout, generator=g) * 2 - 1) * bound
+    bm = (torch.rand(cout, generator=g) * 2 - 1) * bound
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    pad = int((k - 1) / 2)
+    hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
+    res = m2 = mulx = None
+    if residual:
+        res = torch.rand((B, cout, hout, wout), generator=g)
+        res = res.to(adt).float()
+    if out2:
+        m2 = torch.rand((B, cout, hout, wout), generator=g).to(adt).float()
+    if mul:
+        mulx = torch.rand((B, cin, hin, win), generator=g).to(adt).float()
+    tc = impl in (L.CONV_TCGEN05, L.CONV_TCGEN05_GATHER)
+    wf_r, wm_r = (wf.to(torch.bfloat16).float(), wm.to(torch.bfloat16).float()) if tc else (wf, wm)
+    want = ref_gated(logical * mulx if mul else logical, wf_r, bf, wm_r, bm, scale, shift, k, stride, elu, res)
+
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(d, adt)
+    dsc = L.ReadConvDesc()
+    dsc.act_dtype = L.ACT_BF16 if act_bf16 else L.ACT_F32
+    dsc.n_src = len(srcs)
+    keep = []
+    modes = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_UP, "bil4": L.SRC_BILINEAR_UP4}
+    for i, (x, (c, h, w, m, f)) in enumerate(zip(xs, srcs)):
+        t = nhwc(x)
+        keep.append(t)
+        dsc.src[i].ptr, dsc.src[i].C, dsc.src[i].H, dsc.src[i].W = t.data_ptr(), c, h, w
+        dsc.src[i].mode, dsc.src[i].factor = modes[m], f
+    dsc.B, dsc.Hin, dsc.Win, dsc.Cin = B, hin, win, cin
+    dsc.Hout, dsc.Wout, dsc.Cout = hout, wout, cout
+    dsc.k, dsc.stride, dsc.pad, dsc.elu = k, stride, pad, int(elu)
+    dv = [t.to(d).contiguous() for t in (wf, wm, bf, bm, scale, shift)]
+    keep += dv
+    dsc.bias_f, dsc.bias_m, dsc.bn_scale, dsc.bn_shift = (t.data_ptr() for t in dv[2:])
+    stream = L.stream_ptr()
+    if impl == L.CONV_TCGEN05:
+        wt = torch.empty(lib.read_tc_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=d)
+        L.check(lib.read_pack_weights_tc(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, wt.data_ptr(), stream))
+        dsc.w_tc = wt.data_ptr()
+        keep.append(wt)
+    elif impl == L.CONV_TCGEN05_GATHER:
+        wt = torch.empty(lib.read_tcg_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=d)
+        L.check(lib.read_pack_weights_tcg(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, wt.data_ptr(), stream))
+        dsc.w_tc = wt.data_ptr()
+        keep.append(wt)
+    else:
+        npad, kpad = lib.read_generic_npad(cout), ((k * k * cin + 15) // 16) * 16
+        wg = torch.empty(npad * kpad, dtype=torch.float32, device=d)
+        L.check(lib.read_pack_weights_generic(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, wg.data_ptr(), stream))
+        dsc.w_generic = wg.data_ptr()
+        keep.append(wg)
+    dsc.impl = impl
+    if final:
+        out = torch.full((B, cout, hout, wout), float("nan"), dtype=torch.float32, device=d)
+        dsc.out_mode = L.OUT_NCHW_F32
+    else:
+        out = torch.full((B, hout, wout, cout), float("nan"), dtype=adt, device=d)
+        dsc.out_mode = L.OUT_NHWC
+    dsc.out = out.data_ptr()
+    if residual:
+        r = nhwc(res); keep.append(r); dsc.residual = r.data_ptr()
+    o2 = None
+    if out2:
+        mm = nhwc(m2); keep.append(mm)
+        o2 = torch.full_like(out, float("nan"))
+        dsc.out2, dsc.out2_mul = o2.data_ptr(), mm.data_ptr()
+    if mul:
+        mx = nhwc(mulx); keep.append(mx); dsc.mul = mx.data_ptr()
+    plan = L.c_vp()
+    L.check(lib.read_conv_plan_create(ctypes.byref(dsc), ctypes.byref(plan)))
+    assert lib.read_conv_plan_impl(plan) == impl
+    L.check(lib.read_conv_plan_launch(plan, stream))
+    torch.cuda.synchronize()
+    lib.read_conv_plan_destroy(plan)
+    got = out.float().cpu() if final else out.float().permute(0, 3, 1, 2).cpu()
+    if out2:
+        return got, want, o2.float().permute(0, 3, 1, 2).cpu(), want.to(adt).float() * m2
+    return got, want
+
+
+GEN = L.CONV_GENERIC
+TC = L.CONV_TCGEN05
+
+# every distinct layer kind of the net (SURVEY.md §8a census), at small spatial sizes incl. ragged tiles
+GENERIC_CASES = [
+    ("3x3 8->32 first conv", [(8, 20, 28, "id", 1)], 32, 3, 1, True, {}),
+    ("3x3 32->32 ELU", [(32, 17, 23, "id", 1)], 32, 3, 1, True, {}),
+    ("3x3 64->64 noact + residual", [(64, 16, 16, "id", 1)], 64, 3, 1, False, {"residual": True}),
+    ("3x3 s2 32->64 + FAM product output", [(32, 16, 24, "id", 1)], 64, 3, 2, True, {"out2": True}),
+    ("4x4 s2 64->32", [(64, 16, 16, "id", 1)], 32, 4, 2, True, {}),
+    ("1x1 16->32", [(16, 9, 13, "id", 1)], 32, 1, 1, True, {}),
+    ("1x1 32->56 ragged Cout", [(32, 8, 8, "id", 1)], 56, 1, 1, True, {}),
+    ("SCM concat 8+56 -> 64 1x1", [(8, 10, 12, "id", 1), (56, 10, 12, "id", 1)], 64, 1, 1, False, {}),
+    ("AFF0 480->32: id, up2, up4, up8", [(32, 16, 16, "id", 1), (64, 8, 8, "up", 2), (128, 4, 4, "up", 4), (256, 2, 2, "up", 8)], 32, 1, 1, True, {}),
+    ("AFF2 480->128: down4, down2, id, up2", [(32, 16, 16, "down", 4), (64, 8, 8, "down", 2), (128, 4, 4, "id", 1), (256, 2, 2, "up", 2)], 128, 1, 1, True, {}),
+    ("decoder merge: bilinear x4 + id, 256->128", [(128, 3, 5, "bil4", 4), (128, 12, 20, "id", 1)], 128, 1, 1, True, {}),
+    ("final 32->3 NCHW f32", [(32, 16, 24, "id", 1)], 3, 3, 1, False, {"final": True}),
+    ("FAM product on the input side", [(32, 9, 9, "id", 1)], 32, 3, 1, False, {"mul": True, "residual": True}),
+]
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES, ids=[c[0] for c in GENERIC_CASES])
+def test_generic_fp32_matches_torch(case):
+    _, srcs, cout, k, stride, elu, kw = case
+    r = run_conv(srcs, cout, k, stride, elu, False, GEN, **kw)
+    err = float((r[0] - r[1]).abs().max())
+    assert err < 2e-5, err                                 # fp32 math, only summation order differs
+    if kw.get("out2"):
+        assert float((r[2] - r[3]).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES[:6], ids=[c[0] for c in GENERIC_CASES[:6]])
+def test_generic_bf16_activations(case):
+    _, srcs, cout, k, stride, elu, kw = case
+    r = run_conv(srcs, cout, k, stride, elu, True, GEN, **kw)
+    # inputs are bf16-exact, math fp32: the only error is the final bf16 rounding of the output (2^-9 relative)
+    tol = 2 ** -8 * float(r[1].abs().max()) + 1e-3
+    assert float((r[0] - r[1]).abs().max()) < tol
+
+
+TC_CASES = [
+    ("C32 16x32 exact tiles", [(32, 16, 32, "id", 1)], 32, 3, True, {}),
+    ("C32 ragged 19x23", [(32, 19, 23, "id", 1)], 32, 3, False, {"residual": True}),
+    ("C64 24x40", [(64, 24, 40, "id", 1)], 64, 3, True, {}),
+    ("C64 ragged + residual", [(64, 9, 17, "id", 1)], 64, 3, False, {"residual": True}),
+    ("C128 two k-chunks", [(128, 16, 16, "id", 1)], 128, 3, True, {}),
+    ("C256 two n-tiles, four k-chunks", [(256, 10, 18, "id", 1)], 256, 3, False, {"residual": True}),
+    ("C64 1x1", [(64, 8, 16, "id", 1)], 64, 1, True, {}),
+    ("C32 -> 64 channels, FAM product output", [(32, 16, 16, "id", 1)], 64, 3, True, {"out2": True}),
+    ("many tiles per CTA (persistence, phases wrap)", [(32, 200, 208, "id", 1)], 32, 3, True, {"residual": True}),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tcgen05_matches_torch(case):
+    _, srcs, cout, k, elu, kw = case
+    r = run_conv(srcs, cout, k, 1, elu, True, TC, **kw)
+    got, want = r[0], r[1]
+    assert torch.isfinite(got).all(), "tcgen05 kernel left outputs unwritten (NaN sentinel)"
+    # bf16 operands are exact in the reference (weights/inputs pre-rounded), accumulation fp32 on both sides:
+    # error = output bf16 rounding + approx ex2/tanh (~1e-3 abs)
+    tol = 2 ** -8 * float(want.abs().max()) + 4e-3
+    err = float((got - want).abs().max())
+    assert err < tol, (err, tol)
+    if kw.get("out2"):
+        assert float((r[2] - r[3]).abs().max()) < tol
+
+
+GATHER = L.CONV_TCGEN05_GATHER
+GATHER_CASES = [c for c in GENERIC_CASES if not c[6].get("mul")] + [
+    ("3x3 C64 stride 1 (also a TMA shape)", [(64, 24, 40, "id", 1)], 64, 3, 1, True, {"residual": True}),
+    ("SCM0 tail 128->248 (Cout padded to 256, two n-tiles)", [(128, 9, 11, "id", 1)], 248, 1, 1, True, {}),
+    ("3x3 s2 128->256", [(128, 16, 16, "id", 1)], 256, 3, 2, True, {"out2": True}),
+    ("4x4 s2 256->128", [(256, 16, 16, "id", 1)], 128, 4, 2, True, {}),
+    ("many tiles (phases wrap), s2", [(32, 256, 320, "id", 1)], 64, 3, 2, True, {}),
+]
+
+
+@pytest.mark.parametrize("case", GATHER_CASES, ids=[c[0] for c in GATHER_CASES])
+def test_tcgen05_gather_matches_torch(case):
+    _, srcs, cout, k, stride, elu, kw = case
+    r = run_conv(srcs, cout, k, stride, elu, True, GATHER, **kw)
+    got, want = r[0], r[1]
+    assert torch.isfinite(got).all(), "gather kernel left outputs unwritten (NaN sentinel)"
+    # bilinear sources are blended in fp32 then rounded to bf16 before the MMA (the reference blends in fp32): + 2^-8
+    tol = 2 ** -7 * float(want.abs().max()) + 4e-3
+    err = float((got - want).abs().max())
+    assert err < tol, (err, tol)
+    if kw.get("out2"):
+        assert float((r[2] - r[3]).abs().max()) < tol
+
+
+def test_tc_supported_predicate():
+    lib = L.load()
+    d = L.ReadConvDesc()
+    d.act_dtype, d.n_src = L.ACT_BF16, 1
+    d.src[0].mode = L.SRC_IDENTITY
+    d.k, d.stride, d.pad, d.out_mode = 3, 1, 1, L.OUT_NHWC
+    d.Hin = d.Hout = 8
+    d.Win = d.Wout = 8
+    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]:
+        d.Cin, d.Cout = cin, cout
+        assert lib.read_conv_tc_supported(ctypes.byref(d)) == ok, (cin, cout)
+    d.Cin = d.Cout = 32
+    d.act_dtype = L.ACT_F32
+    assert lib.read_conv_tc_supported(ctypes.byref(d)) == 0
