@@ -316,8 +316,11 @@ def run_ours(args):
 
     sp = L.stream_ptr()
     tc_ms = tc_flops = gen_ms = gen_flops = tcg_ms = tcg_flops = 0.0
+    layer_rows = []
     for ly in eng.layers:
         t = time_call(lambda ly=ly: L.check(lib.read_conv_plan_launch(ly.plan, sp)), reps=4)
+        layer_rows.append({"name": ly.name, "impl": int(ly.impl), "ms": t, "gflop": ly.flops / 1e9,
+                           "tflops": ly.flops / (t * 1e-3) / 1e12})
         if ly.impl == L.CONV_TCGEN05:
             tc_ms += t; tc_flops += ly.flops
         elif ly.impl == L.CONV_TCGEN05_GATHER:
@@ -371,6 +374,9 @@ def run_ours(args):
     gen_ach = gen_flops / (gen_ms * 1e-3) / 1e12 if gen_ms > 0 else None
     tcg_ach = tcg_flops / (tcg_ms * 1e-3) / 1e12 if tcg_ms > 0 else None
 
+    if rank == 0 and args.layer_times:
+        os.makedirs(os.path.dirname(os.path.abspath(args.layer_times)), exist_ok=True)
+        json.dump(layer_rows, open(args.layer_times, "w"), indent=0)
     if rank == 0:
         import torch as _t
         cpu_line = None
@@ -418,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-times", default=None, help="write per-layer CUDA-event timings (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

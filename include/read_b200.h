@@ -113,6 +113,13 @@ int read_gather_from_index(const float *tex_nd, int D, int64_t N, const float *i
 /* Fused path: straight from the packed z-buffer level (skips the float index map). */
 int read_gather_from_zbuf(const float *tex_nd, int D, int64_t N, const uint64_t *zbuf_level, int B, int h,
                           int w, int layout, int activation, void *out, void *stream);
+/* Per-frame fast path for a 4-level NESTED pyramid (every level an exact half of the previous one, W,H % 8 == 0)
+ * and D == 8: one kernel derives levels 1..3 from level 0 (bit-identical 2x2 min), stores them, gathers all four
+ * feature maps (NHWC bf16 or f32; outs = HOST array of 4 device pointers) and, if reset_level0, leaves level 0
+ * cleared for the next frame.  Views [view0, view0+nviews) of the B-view pyramid are processed (outs hold nviews views).
+ * Call after read_raster_project_direct (replaces derive + 4 gathers + next clear). */
+int read_pyramid_resolve_gather(const float *tex_nd, int D, int64_t N, uint64_t *zbuf, int B, int view0, int nviews,
+                                int W, int H, int L, int layout, void *const *outs, int reset_level0, void *stream);
 /* Backward of the gather (autograd of index_select, texture.py:61): grad_tex_nd[ids[p], :] += grad_out[.., p]
  * grad_out is NCHW f32 [B,D,h,w]; grad_tex_nd [N,D] f32 accumulates (caller zeroes).  Empty pixels carry
  * id 0, so point 0 receives their gradient exactly like the reference. */

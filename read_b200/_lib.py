@@ -60,6 +60,8 @@ _SIGS = {
     "read_texture_to_channel_major": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
     "read_gather_from_index": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_gather_from_zbuf": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_pyramid_resolve_gather": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            ctypes.POINTER(c_vp), c_int, c_vp]),
     "read_gather_backward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp]),
     "read_generic_npad": (c_int, [c_int]),
     "read_pack_weights_generic": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),

@@ -5,20 +5,24 @@
 //
 //   GEMM view   D[M = 128 output pixels (8 rows x 16 cols of one image), N = f|m channels] +=
 //               A[M, K = one filter tap x CIN_BLK input channels] * B[N, K]
-//   A operand   TMA 4-D tile load {c, x, y, b} of the input at the tap-shifted position; rows/cols
-//               outside the image are ZERO-FILLED by the TMA unit == the conv's zero padding
-//               (unet.py:29,36: padding=int((k-1)/2), zeros).  Lands in smem as 128 pixel rows of
-//               CIN_BLK bf16 (64 or 128 bytes) with the matching 64B/128B swizzle: exactly the canonical
-//               K-major UMMA operand layout, so no im2col is ever materialised.
-//   B operand   packed weights [tap][kchunk][n][CIN_BLK] bf16, conv_f and conv_m side by side in N so
-//               ONE accumulator tile holds both gates of the same output channels.
+//   A operand   ONE TMA 4-D tile load {c, x, y, b} per filter COLUMN kx: a (8+k-1)-row x 16-col halo tile at the
+//               kx-shifted position; the k filter ROWS reuse it through UMMA descriptors whose start address is
+//               advanced by ky*16 pixel rows (a whole number of swizzle atoms), so the input is fetched from L2
+//               k times per tile instead of k*k times.  Pixels outside the image are ZERO-FILLED by the TMA unit
+//               == the conv's zero padding (unet.py:29,36).  Rows are CIN_BLK bf16 (64 or 128 bytes) with the
+//               matching 64B/128B swizzle: the canonical K-major UMMA layout, no im2col is ever materialised.
+//   B operand   packed weights [tap][kchunk][n][CIN_BLK] bf16, conv_f and conv_m side by side in N so ONE
+//               accumulator tile holds both gates of the same output channels.  When the whole layer fits
+//               (<= 144 KB: the C=32 and C=64 layers) the weights are loaded ONCE per CTA and stay resident in
+//               shared memory; otherwise they stream through their own mbarrier ring.
 //   D           fp32 in TMEM, double buffered (2 x up to 256 columns): the epilogue of tile i overlaps the
 //               MMAs of tile i+1.
 //   epilogue    tcgen05.ld -> bias, ELU, sigmoid gate, BN affine, residual add, bf16 pack -> global
 //               (optionally a second output y*z for the following FAM, unet.py:115).
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
-// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quadrant = warp%4).
+// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quadrant = warp%4).  The two single-thread roles keep
+// their ring indices/phases incrementally: no integer division on the per-k-step path.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "ptx.cuh"
@@ -32,7 +36,11 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_TW = 16, TC_TH = 8;          // 128-pixel M tile
 constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr uint32_t TC_RESIDENT_MAX = 144 * 1024;
 constexpr int TC_TMEM_COLS = 512;
+// barrier slots (uint64 each)
+constexpr int BAR_AFULL = 0, BAR_AEMPTY = 8, BAR_BFULL = 16, BAR_BEMPTY = 24, BAR_TFULL = 32, BAR_TEMPTY = 34,
+              BAR_BRES = 36, BAR_TMEMPTR = 38, BAR_PARAMS = 40;
 
 struct TcArgs {
     int B, H, W, Cin, Cout;
@@ -40,8 +48,8 @@ struct TcArgs {
     int cin_blk, kchunks;
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
-    int stages;
-    uint32_t a_bytes, b_bytes;
+    int a_stages, b_stages, b_resident;
+    uint32_t a_bytes, b_bytes, b_region_off;   // halo tile bytes, one weight tile bytes, byte offset of the B region
     int elu;
     const float *bias_f, *bias_m, *scale, *shift;
     const __nv_bfloat16 *residual;
@@ -69,16 +77,16 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
 
-    const uint32_t stage_bytes = a.a_bytes + a.b_bytes;
-    const uint32_t ring_bytes = stage_bytes * (uint32_t)a.stages;
-    // barriers + tmem pointer live after the ring
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + ring_bytes);
-    const uint32_t full0 = s_u32(bars);                       // [TC_MAX_STAGES]
-    const uint32_t empty0 = full0 + 8 * TC_MAX_STAGES;        // [TC_MAX_STAGES]
-    const uint32_t tfull0 = empty0 + 8 * TC_MAX_STAGES;       // [2]
-    const uint32_t tempty0 = tfull0 + 16;                     // [2]
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TC_MAX_STAGES + 4);
-    float *s_par = reinterpret_cast<float *>(bars + 2 * TC_MAX_STAGES + 6);   // 4 x Cout floats
+    const int ntaps = a.ksize * a.ksize;
+    const uint32_t b_region = smem_base + a.b_region_off;
+    const uint32_t b_region_bytes = a.b_resident ? (uint32_t)(ntaps * a.kchunks) * a.b_bytes : (uint32_t)a.b_stages * a.b_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + b_region_bytes);
+    const uint32_t bar0 = s_u32(bars);
+    const uint32_t afull0 = bar0 + 8 * BAR_AFULL, aempty0 = bar0 + 8 * BAR_AEMPTY;
+    const uint32_t bfull0 = bar0 + 8 * BAR_BFULL, bempty0 = bar0 + 8 * BAR_BEMPTY;
+    const uint32_t tfull0 = bar0 + 8 * BAR_TFULL, tempty0 = bar0 + 8 * BAR_TEMPTY, bres = bar0 + 8 * BAR_BRES;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + BAR_TMEMPTR);
+    float *s_par = reinterpret_cast<float *>(bars + BAR_PARAMS);   // 4 x Cout floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -93,14 +101,17 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+        for (int s = 0; s < TC_MAX_STAGES; ++s) {
+            mbar_init(afull0 + 8 * s, 1);
+            mbar_init(aempty0 + 8 * s, 1);
+            mbar_init(bfull0 + 8 * s, 1);
+            mbar_init(bempty0 + 8 * s, 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, 4);   // one arrival per epilogue warp
         }
+        mbar_init(bres, 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(s_u32(tmem_ptr_smem), TC_TMEM_COLS);
@@ -111,13 +122,16 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     const int m_tiles = a.tiles_x * a.tiles_y * a.B;
     const long long total_tiles = (long long)m_tiles * a.n_tiles;
-    const int ntaps = a.ksize * a.ksize;
-    const int ksteps = ntaps * a.kchunks;
     const int n_total = a.n_tile * a.n_tiles;
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        uint32_t it = 0;
+        if (a.b_resident) {
+            const int nb = ntaps * a.kchunks;
+            mbar_arrive_expect_tx(bres, (uint32_t)nb * a.b_bytes);
+            for (int i = 0; i < nb; ++i) tma_load_2d(&tmB, bres, b_region + (uint32_t)i * a.b_bytes, 0, i * n_total);
+        }
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int nt = (int)(t % a.n_tiles);
             int mt = (int)(t / a.n_tiles);
@@ -125,17 +139,23 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mt /= a.tiles_x;
             const int ty = mt % a.tiles_y;
             const int b = mt / a.tiles_y;
-            const int x0 = tx * TC_TW, y0 = ty * TC_TH;
-            for (int tap = 0; tap < ntaps; ++tap) {
-                const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
-                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    const uint32_t fb = full0 + 8 * s;
-                    mbar_arrive_expect_tx(fb, stage_bytes);
-                    const uint32_t sa = smem_base + s * stage_bytes;
-                    tma_load_4d(&tmA, fb, sa, kc * a.cin_blk, x0 + kx - a.pad, y0 + ky - a.pad, b);
-                    tma_load_2d(&tmB, fb, sa + a.a_bytes, 0, (tap * a.kchunks + kc) * n_total + nt * a.n_tile);
+            const int x0 = tx * TC_TW - a.pad, y0 = ty * TC_TH - a.pad;
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+                for (int kx = 0; kx < a.ksize; ++kx) {
+                    mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+                    mbar_arrive_expect_tx(afull0 + 8 * as, a.a_bytes);
+                    tma_load_4d(&tmA, afull0 + 8 * as, smem_base + as * a.a_bytes, kc * a.cin_blk, x0 + kx, y0, b);
+                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; }
+                    if (!a.b_resident) {
+                        int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*ksize + kx
+                        const int row_step = a.ksize * a.kchunks * n_total;
+                        for (int ky = 0; ky < a.ksize; ++ky, row += row_step) {
+                            mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+                            mbar_arrive_expect_tx(bfull0 + 8 * bs, a.b_bytes);
+                            tma_load_2d(&tmB, bfull0 + 8 * bs, b_region + bs * a.b_bytes, 0, row);
+                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; }
+                        }
+                    }
                 }
             }
         }
@@ -143,26 +163,48 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t layout_type = (a.cin_blk == 64) ? 2u : 4u;
-        const uint32_t sbo = 8u * (uint32_t)a.cin_blk * 2u;   // 8 rows of the swizzle atom
-        uint32_t it = 0, tile_it = 0;
+        const uint32_t row_bytes = (uint32_t)a.cin_blk * 2u;
+        const uint32_t sbo = 8u * row_bytes;                      // 8 rows = one swizzle atom
+        const uint64_t desc_hi = make_kmajor_desc(0, sbo, layout_type);
+        const uint32_t ky_step = (TC_TW * row_bytes) >> 4;        // one tile row of pixels, in 16-byte units
+        const int kk_n = a.cin_blk / 16;
+        if (a.b_resident) mbar_wait(bres, 0);
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0, tile_it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
             const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256u;
-            for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
-                tcgen05_fence_after();
-                const uint32_t sa = smem_base + s * stage_bytes;
-                const uint64_t adesc = make_kmajor_desc(sa, sbo, layout_type);
-                const uint64_t bdesc = make_kmajor_desc(sa + a.a_bytes, sbo, layout_type);
-                const int kk_n = a.cin_blk / 16;
-                for (int kk = 0; kk < kk_n; ++kk) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                    umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0 ? 1u : 0u);
+            uint32_t first = 0;                                   // 0 until the first MMA of this tile was issued
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+                for (int kx = 0; kx < a.ksize; ++kx) {
+                    mbar_wait(afull0 + 8 * as, aph);
+                    tcgen05_fence_after();
+                    const uint64_t adesc0 = desc_hi | (uint64_t)(((smem_base + as * a.a_bytes) & 0x3FFFFu) >> 4);
+                    for (int ky = 0; ky < a.ksize; ++ky) {
+                        uint32_t baddr;
+                        if (a.b_resident) {
+                            baddr = b_region + (uint32_t)((ky * a.ksize + kx) * a.kchunks + kc) * a.b_bytes;
+                        } else {
+                            mbar_wait(bfull0 + 8 * bs, bph);
+                            tcgen05_fence_after();
+                            baddr = b_region + bs * a.b_bytes;
+                        }
+                        const uint64_t adesc = adesc0 + (uint64_t)(ky * ky_step);
+                        const uint64_t bdesc = desc_hi | (uint64_t)((baddr & 0x3FFFFu) >> 4);
+                        for (int kk = 0; kk < kk_n; ++kk) {
+                            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, first);
+                            first = 1u;
+                        }
+                        if (!a.b_resident) {
+                            umma_commit(bempty0 + 8 * bs);
+                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                    umma_commit(aempty0 + 8 * as);
+                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; }
                 }
-                umma_commit(empty0 + 8 * s);
             }
             umma_commit(tfull0 + 8 * acc);
         }
@@ -349,11 +391,12 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     TcPlan *p = new (std::nothrow) TcPlan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
 
+    const int halo_rows = TC_TH + d.k - 1;
     const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    {   // activations: dims {C, W, H, B}
+    {   // activations: dims {C, W, H, B}; box = one halo tile for one filter column
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, TC_TW, TC_TH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, TC_TW, (cuuint32_t)halo_rows, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.src[0].ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -364,7 +407,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
             return READ_ERR_CUDA;
         }
     }
-    {   // weights: dims {cin_blk, ksteps * n_total}
+    {   // weights: dims {cin_blk, taps * kchunks * n_total}
         const cuuint64_t rows = (cuuint64_t)d.k * d.k * g.kchunks * 2 * d.Cout;
         cuuint64_t dims[2] = {(cuuint64_t)g.cin_blk, rows};
         cuuint64_t strides[1] = {(cuuint64_t)g.cin_blk * 2};
@@ -385,18 +428,30 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.cin_blk = g.cin_blk; a.kchunks = g.kchunks; a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
     a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
     a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
-    a.a_bytes = 128u * g.cin_blk * 2u;
+    a.a_bytes = (uint32_t)halo_rows * TC_TW * g.cin_blk * 2u;
     a.b_bytes = (uint32_t)g.n_tile * g.cin_blk * 2u;
-    int stages = (int)(TC_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    a.stages = stages;
+    const uint32_t total_b = (uint32_t)(d.k * d.k * g.kchunks) * a.b_bytes;
+    a.b_resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b >= 2 * a.a_bytes) ? 1 : 0;
+    uint32_t b_region_bytes;
+    if (a.b_resident) {
+        int st = (int)((TC_SMEM_BUDGET - total_b) / a.a_bytes);
+        a.a_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+        a.b_stages = 0;
+        b_region_bytes = total_b;
+    } else {
+        a.a_stages = 3;
+        int st = (int)((TC_SMEM_BUDGET - 3 * a.a_bytes) / a.b_bytes);
+        a.b_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+        b_region_bytes = (uint32_t)a.b_stages * a.b_bytes;
+    }
+    a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
     a.out = static_cast<__nv_bfloat16 *>(d.out);
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
-    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * TC_MAX_STAGES + 6) + 16 * (size_t)d.Cout + 64;
+    p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + 8 * BAR_PARAMS + 16 * (size_t)d.Cout + 64;
     *out = p;
     return READ_OK;
 }

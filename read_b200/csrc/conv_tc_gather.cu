@@ -34,7 +34,7 @@ constexpr int G_LA = 2;                        // cp.async groups kept in flight
 
 struct GSrc {
     const __nv_bfloat16 *ptr;
-    int C, H, W, mode, factor, c_begin;
+    int C, H, W, mode, shift, c_begin;   // shift = log2(resample factor)
 };
 
 struct GArgs {
@@ -98,6 +98,22 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CP = a.Cout_pad;
+    // per-(K block, 16-byte chunk) decode table, built once per CTA so the producers' hot loop has no division:
+    // {source index (-1 = zero padding of K), ky, kx, channel offset inside the source}
+    int4 *s_tab = reinterpret_cast<int4 *>(s_par + 4 * CP);
+    for (int i = threadIdx.x; i < a.kblocks * 8; i += G_THREADS) {
+        const int kel = i * 8;
+        int4 e = make_int4(-1, 0, 0, 0);
+        if (kel < a.K) {
+            const int tap = kel / a.Cin;
+            const int c = kel - tap * a.Cin;
+            int si = 0;
+            for (int q = 1; q < READ_MAX_SRC; ++q)
+                if (q < a.n_src && c >= a.src[q].c_begin) si = q;
+            e = make_int4(si, tap / a.ksize, tap % a.ksize, c - a.src[si].c_begin);
+        }
+        s_tab[i] = e;
+    }
     for (int i = threadIdx.x; i < CP; i += G_THREADS) {
         const bool v = i < a.Cout;
         s_par[i] = v ? a.bias_f[i] : 0.f;
@@ -130,15 +146,16 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     if (warp == 0) {
         if (lane == 0) {
             // ===================== weight TMA producer =====================
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = (int)(t % a.n_tiles);
-                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                int row = nt * a.n_tile;
+                for (int kb = 0; kb < a.kblocks; ++kb, row += n_total) {
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const uint32_t fb = full0 + 8 * s;
                     mbar_arrive_expect_tx(fb, a.b_bytes);
-                    tma_load_2d(&tmB, fb, smem_base + s * stage_bytes + a.a_bytes, 0, kb * n_total + nt * a.n_tile);
+                    tma_load_2d(&tmB, fb, smem_base + s * stage_bytes + a.a_bytes, 0, row);
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -146,14 +163,13 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         if (lane == 0) {
             // ===================== MMA issuer =====================
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t it = 0, tile_it = 0;
+            uint32_t s = 0, ph = 0, tile_it = 0;
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
                 const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256u;
-                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
+                for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(full0 + 8 * s, ph);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + s * stage_bytes;
@@ -163,6 +179,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                     for (int kk = 0; kk < G_KBLK / 16; ++kk)
                         umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
                     umma_commit(empty0 + 8 * s);
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(tfull0 + 8 * acc);
             }
@@ -173,6 +190,8 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         const int j = t & 7;                // 16-byte chunk inside the 128-byte K row
         const int px = t >> 3;              // tile column handled by this thread (rows r = px + 16*i, i = tile row)
         const uint32_t dst_off = (uint32_t)px * 128u + (uint32_t)((j ^ (px & 7)) << 4);
+        uint32_t s = 0, ph = 0;           // ring slot being filled and its phase
+        uint32_t pub = 0;                 // ring slot to publish next (lags G_LA steps behind)
         uint32_t it = 0;
         for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
             int mt = (int)(tl / a.n_tiles);
@@ -181,44 +200,36 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             const int ty = mt % a.tiles_y;
             const int b = mt / a.tiles_y;
             const int ox = tx * G_TW + px, oy0 = ty * G_TH;
+            const int ixb = ox * a.stride - a.pad, iyb = oy0 * a.stride - a.pad;
+            const bool colok = ox < a.Wout;
+            const int rows_ok = a.Hout - oy0;
             for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                const uint32_t s = it % (uint32_t)a.stages, ph = (it / (uint32_t)a.stages) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t dst0 = smem_base + s * stage_bytes + dst_off;
-                const int kel = (kb * 8 + j) * 8;
-                bool kvalid = kel < a.K;
-                int ky = 0, kx = 0, si = 0, cl = 0;
-                if (kvalid) {
-                    const int tap = kel / a.Cin;
-                    const int c = kel - tap * a.Cin;
-                    ky = tap / a.ksize;
-                    kx = tap - ky * a.ksize;
-#pragma unroll
-                    for (int q = 1; q < READ_MAX_SRC; ++q)
-                        if (q < a.n_src && c >= a.src[q].c_begin) si = q;
-                    cl = c - a.src[si].c_begin;
-                }
-                const GSrc &sv = a.src[si];
-                const int ix = ox * a.stride - a.pad + kx;
-                const bool xvalid = kvalid && (ox < a.Wout) && (ix >= 0) && (ix < a.Win);
-                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.H * sv.W * sv.C + cl;
+                const int4 e = s_tab[kb * 8 + j];
+                const GSrc &sv = a.src[e.x < 0 ? 0 : e.x];
+                const int ix = ixb + e.z;
+                const bool xvalid = (e.x >= 0) && colok && (ix >= 0) && (ix < a.Win);
+                const int iy0 = iyb + e.y;
+                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.H * sv.W * sv.C + e.w;
                 if (sv.mode != READ_SRC_BILINEAR_UP4) {
                     int sx = ix;
-                    if (sv.mode == READ_SRC_NEAREST_DOWN) sx = ix * sv.factor;
-                    else if (sv.mode == READ_SRC_NEAREST_UP) sx = ix / sv.factor;
+                    if (sv.mode == READ_SRC_NEAREST_DOWN) sx = ix << sv.shift;
+                    else if (sv.mode == READ_SRC_NEAREST_UP) sx = ix >> sv.shift;
                     sx = sx < sv.W ? sx : sv.W - 1;
                     sx = sx < 0 ? 0 : sx;
+                    const __nv_bfloat16 *colp = sbase + (long long)sx * sv.C;
+                    const long long rowstride = (long long)sv.W * sv.C;
 #pragma unroll
                     for (int i = 0; i < G_TH; ++i) {
-                        const int oy = oy0 + i;
-                        const int iy = oy * a.stride - a.pad + ky;
-                        const bool valid = xvalid && (oy < a.Hout) && (iy >= 0) && (iy < a.Hin);
+                        const int iy = iy0 + i * a.stride;
+                        const bool valid = xvalid && (i < rows_ok) && (iy >= 0) && (iy < a.Hin);
                         int sy = iy;
-                        if (sv.mode == READ_SRC_NEAREST_DOWN) sy = iy * sv.factor;
-                        else if (sv.mode == READ_SRC_NEAREST_UP) sy = iy / sv.factor;
+                        if (sv.mode == READ_SRC_NEAREST_DOWN) sy = iy << sv.shift;
+                        else if (sv.mode == READ_SRC_NEAREST_UP) sy = iy >> sv.shift;
                         sy = sy < sv.H ? sy : sv.H - 1;
                         sy = sy < 0 ? 0 : sy;
-                        const __nv_bfloat16 *p = sbase + ((long long)sy * sv.W + sx) * sv.C;
+                        const __nv_bfloat16 *p = colp + sy * rowstride;
                         cp_async16(dst0 + (uint32_t)i * 2048u, valid ? (const void *)p : (const void *)sv.ptr, valid ? 16u : 0u);
                     }
                 } else {
@@ -230,9 +241,8 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                     const float lx = fx - (float)x0, hx = 1.f - lx;
 #pragma unroll 2
                     for (int i = 0; i < G_TH; ++i) {
-                        const int oy = oy0 + i;
-                        const int iy = oy * a.stride - a.pad + ky;
-                        const bool valid = xvalid && (oy < a.Hout) && (iy >= 0) && (iy < a.Hin);
+                        const int iy = iy0 + i * a.stride;
+                        const bool valid = xvalid && (i < rows_ok) && (iy >= 0) && (iy < a.Hin);
                         uint4 o = make_uint4(0, 0, 0, 0);
                         if (valid) {
                             float fy = 0.25f * ((float)iy + 0.5f) - 0.5f;
@@ -248,9 +258,9 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                             const uint32_t *a00 = &v00.x, *a01 = &v01.x, *a10 = &v10.x, *a11 = &v11.x;
                             uint32_t r[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f00 = g_unpack2(a00[e]), f01 = g_unpack2(a01[e]), f10 = g_unpack2(a10[e]), f11 = g_unpack2(a11[e]);
-                                r[e] = g_pack2(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f00 = g_unpack2(a00[q]), f01 = g_unpack2(a01[q]), f10 = g_unpack2(a10[q]), f11 = g_unpack2(a11[q]);
+                                r[q] = g_pack2(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
                                                hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
                             }
                             o = make_uint4(r[0], r[1], r[2], r[3]);
@@ -264,15 +274,20 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 if (it >= (uint32_t)G_LA) {
                     cp_async_wait<G_LA>();
                     fence_proxy_async();
-                    mbar_arrive(full0 + 8 * ((it - G_LA) % (uint32_t)a.stages));
+                    mbar_arrive(full0 + 8 * pub);
+                    if (++pub == (uint32_t)a.stages) pub = 0;
                 }
+                if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
             }
         }
         // drain: publish the last min(it, G_LA) stages
         cp_async_wait<0>();
         fence_proxy_async();
-        const uint32_t first = it >= (uint32_t)G_LA ? it - G_LA : 0u;
-        for (uint32_t k = first; k < it; ++k) mbar_arrive(full0 + 8 * (k % (uint32_t)a.stages));
+        const uint32_t left = it < (uint32_t)G_LA ? it : (uint32_t)G_LA;
+        for (uint32_t k = 0; k < left; ++k) {
+            mbar_arrive(full0 + 8 * pub);
+            if (++pub == (uint32_t)a.stages) pub = 0;
+        }
     } else {
         // ===================== epilogue (warps 6-9) =====================
         const int q = warp & 3;
@@ -413,8 +428,12 @@ bool tcg_supported(const read_conv_desc &d)
 {
     if (d.act_dtype != READ_ACT_BF16 || d.mul != nullptr) return false;
     if (d.out_mode == READ_OUT_NHWC && d.Cout % 8 != 0) return false;
-    for (int i = 0; i < d.n_src; ++i)
+    for (int i = 0; i < d.n_src; ++i) {
         if (d.src[i].C % 8 != 0) return false;
+        const int f = d.src[i].factor;
+        const bool resampled = d.src[i].mode == READ_SRC_NEAREST_DOWN || d.src[i].mode == READ_SRC_NEAREST_UP;
+        if (resampled && (f < 2 || (f & (f - 1)) != 0)) return false;      // power-of-two factors only (shifts)
+    }
     return g_geom(d.Cin, d.Cout, d.k, nullptr);
 }
 
@@ -463,8 +482,10 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     GArgs &a = p->args;
     int cb = 0;
     for (int i = 0; i < d.n_src; ++i) {
+        int sh = 0;
+        while ((1 << sh) < d.src[i].factor) ++sh;
         a.src[i] = GSrc{static_cast<const __nv_bfloat16 *>(d.src[i].ptr), d.src[i].C, d.src[i].H, d.src[i].W, d.src[i].mode,
-                        d.src[i].factor, cb};
+                        sh, cb};
         cb += d.src[i].C;
     }
     for (int i = d.n_src; i < READ_MAX_SRC; ++i) a.src[i] = a.src[0];
@@ -487,7 +508,7 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     a.out = d.out; a.out_mode = d.out_mode;
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
-    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 64;
+    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 16 * (size_t)g.kblocks * 8 + 64;
     *out = p;
     return READ_OK;
 }

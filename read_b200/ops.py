@@ -137,6 +137,23 @@ def gather_from_zbuf(tex_nd, pyr, l, layout=L.FEAT_NHWC_BF16, activation="none",
     return out
 
 
+def pyramid_resolve_gather(tex_nd, pyr, outs, layout=L.FEAT_NHWC_BF16, view0=0, nviews=None, reset_level0=False):
+    """Fused per-frame path: derive levels 1..3, gather all 4 feature maps into ``outs`` (list of 4 NHWC tensors holding
+    ``nviews`` views), optionally leave level 0 cleared.  Needs a 4-level nested pyramid and 8-d descriptors; call after
+    ``raster_project(..., derive=False)``."""
+    N, D = tex_nd.shape
+    nviews = pyr.B if nviews is None else nviews
+    if not fused_resolve_supported(pyr, D):
+        raise RuntimeError("read_b200: fused pyramid resolve needs L == 4 nested levels, W,H % 8 == 0 and D == 8")
+    arr = (L.c_vp * 4)(*[o.data_ptr() for o in outs])
+    L.check(L.load().read_pyramid_resolve_gather(tex_nd.data_ptr(), D, N, pyr.buf.data_ptr(), pyr.B, view0, nviews, pyr.W,
+                                                 pyr.H, pyr.L, layout, arr, int(bool(reset_level0)), L.stream_ptr()))
+
+
+def fused_resolve_supported(pyr, D=8):
+    return pyr.L == 4 and D == 8 and pyr.direct_mask == 1 and pyr.W % 8 == 0 and pyr.H % 8 == 0
+
+
 def gather_backward(grad_out, ids, N):
     """grad_out [B,D,h,w] f32, ids [B,h,w] f32 -> grad [N,D] f32 (scatter-add)."""
     grad_out = grad_out.contiguous()
