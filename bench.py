@@ -249,15 +249,14 @@ def run_ours(args):
     def step(m_dev):
         """m_dev [B,4,4] on device -> eng.output [1,3,H,W] on device."""
         if world == 1:
-            pyr.clear()
-            ops.raster_project(pyr, xyz, m_dev)
+            # level 0 is left cleared by the previous frame's fused resolve (reset_level0)
+            ops.raster_project(pyr, xyz, m_dev, derive=False)
+            ops.pyramid_resolve_gather(tex_nd, pyr, eng.inputs, layout, reset_level0=True)
         else:
-            rdist.render_sharded(pyr, xyz, start, m_dev)
-        sp = L.stream_ptr()
-        for l in range(LEVELS):
-            off, w_l, h_l = lvl_views[l]
-            L.check(lib.read_gather_from_zbuf(tex_nd.data_ptr(), 8, N_POINTS, pyr.buf[off:].data_ptr(), 1, h_l, w_l,
-                                              layout, 0, eng.inputs[l].data_ptr(), sp))
+            L.check(lib.read_zbuf_clear(pyr.buf.data_ptr(), pyr.B * W * H, L.stream_ptr()))     # level 0 of all views
+            ops.raster_project(pyr, xyz, m_dev, id_base=start, derive=False)
+            rdist.allreduce_min_(pyr.buf[:pyr.B * W * H])                                        # ONE collective per step
+            ops.pyramid_resolve_gather(tex_nd, pyr, eng.inputs, layout, view0=rank, nviews=1)
         return eng.run()
 
     def barrier():
@@ -289,11 +288,12 @@ def run_ours(args):
         frame_host.copy_(out[0], non_blocking=True)                      # D2H of the frame this rank produced
         torch.cuda.current_stream().synchronize()
 
-    # ---- warm-up (also builds the CUDA graph), counts launches of one eager step
+    # ---- warm-up (also builds the CUDA graph)
+    pyr.clear()
     for s in range(args.warmup):
         resident_step(s)
     torch.cuda.synchronize()
-    launches_per_step = (5 + LEVELS + eng.n_launches()) if world == 1 else (5 + LEVELS + eng.n_launches())
+    launches_per_step = (2 + eng.n_launches()) if world == 1 else (3 + eng.n_launches())   # + NCCL's own kernel
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
@@ -329,34 +329,41 @@ def run_ours(args):
             gen_ms += t; gen_flops += ly.flops
     m0 = mats_dev[args.warmup]
 
-    def raster_only():
-        pyr.clear()
-        ops.raster_project(pyr, xyz, m0)
-
-    def project_only():
+    def raster_frame():                      # what a frame does before the net (level 0 is clean on entry)
         ops.raster_project(pyr, xyz, m0, derive=False)
+        ops.pyramid_resolve_gather(tex_nd, pyr, eng.inputs, layout, view0=rank if world > 1 else 0,
+                                   nviews=1 if world > 1 else None, reset_level0=(world == 1))
+        if world > 1:
+            L.check(lib.read_zbuf_clear(pyr.buf.data_ptr(), pyr.B * W * H, sp))
 
-    def gather_only():
-        for l in range(LEVELS):
-            off, w_l, h_l = lvl_views[l]
-            L.check(lib.read_gather_from_zbuf(tex_nd.data_ptr(), 8, N_POINTS, pyr.buf[off:].data_ptr(), 1, h_l, w_l,
-                                              layout, 0, eng.inputs[l].data_ptr(), sp))
-    raster_ms = time_call(raster_only)
+    def one_shot(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     pyr.clear()
-    project_ms = time_call(project_only, reps=3)      # first rep fills the z-buffer, later reps are early-z only -> use rep 0
-    pyr.clear(); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); project_only(); b.record(); torch.cuda.synchronize()
-    project_ms = a.elapsed_time(b)
-    ops.raster_derive(pyr)
-    gather_ms = time_call(gather_only)
+    rg_ms = time_call(raster_frame, reps=6)
+    # the two halves separately (each on the state the other leaves behind)
+    project_ms = float(np.mean([one_shot(lambda: ops.raster_project(pyr, xyz, m0, derive=False)) +
+                                0 * one_shot(lambda: ops.pyramid_resolve_gather(tex_nd, pyr, eng.inputs, layout, view0=0,
+                                                                                nviews=1, reset_level0=True))
+                                for _ in range(4)][1:]))
+    resolve_ms = 0.0
+    for _ in range(4):
+        ops.raster_project(pyr, xyz, m0, derive=False)
+        resolve_ms += one_shot(lambda: ops.pyramid_resolve_gather(tex_nd, pyr, eng.inputs, layout, view0=0, nviews=1,
+                                                                   reset_level0=True)) / 4
+    if world > 1:
+        pyr.clear()
+    raster_ms, gather_ms = project_ms, resolve_ms
     P = sum(w_l * h_l for (w_l, h_l) in pyr.sizes)
     feat_bytes = 2 if eng.bf16 else 4
     # algorithmic bytes: xyz once + packed z write + descriptor read + feature write
     raster_bytes = 12 * count * 1 + P * B * 8
     gather_bytes = P * (8 + 32 + 8 * feat_bytes)
     rg_bytes = raster_bytes + gather_bytes
-    rg_ms = raster_ms + gather_ms
     hbm = pk["hbm_gbs"]
     tens_peak = pk["bf16_tflops_sustained"]
     roof_tc = None
@@ -367,10 +374,10 @@ def run_ours(args):
                    "peak_src": pk["src"] + " (sustained bf16)", "traffic": None, "ms_per_frame": tc_ms,
                    "layers": sum(1 for l_ in eng.layers if l_.impl == L.CONV_TCGEN05)}
     ach_r = rg_bytes / (rg_ms * 1e-3) / 1e9
-    roof_raster = {"kernel": "raster_project_kernel + zbuf derive + gather_kernel", "bound": "hbm",
+    roof_raster = {"kernel": "raster_project_kernel + pyramid_resolve_gather_kernel", "bound": "hbm",
                    "achieved": ach_r, "peak": hbm, "unit": "GB/s", "frac": ach_r / hbm, "peak_src": pk["src"],
                    "traffic": None, "algorithmic_bytes": rg_bytes, "ms_per_frame": rg_ms,
-                   "project_ms": project_ms, "clear_project_derive_ms": raster_ms, "gather_ms": gather_ms}
+                   "project_ms": project_ms, "resolve_gather_ms": resolve_ms}
     gen_ach = gen_flops / (gen_ms * 1e-3) / 1e12 if gen_ms > 0 else None
     tcg_ach = tcg_flops / (tcg_ms * 1e-3) / 1e12 if tcg_ms > 0 else None
 
@@ -405,7 +412,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof_tc if roof_tc else roof_raster,
             "roofline_raster": roof_raster,
-            "breakdown_ms_per_frame": {"raster_clear_project_derive": raster_ms, "gather": gather_ms,
+            "breakdown_ms_per_frame": {"raster_project": raster_ms, "pyramid_resolve_gather": gather_ms, "raster_total": rg_ms,
                                        "conv_tcgen05_tma": tc_ms, "conv_tcgen05_gather": tcg_ms,
                                        "conv_tcgen05_gather_tflops": tcg_ach, "conv_generic": gen_ms,
                                        "conv_generic_tflops": gen_ach, "net_flops": eng.flops},

@@ -111,12 +111,22 @@ class NetAndTexture(nn.Module):
         pyr = getattr(self, "_pyr", None)
         if pyr is None or (pyr.B, pyr.W, pyr.H, pyr.L) != (B, W, H, n_levels) or pyr.buf.device != xyz.device:
             pyr = self._pyr = ops.Pyramid(B, W, H, n_levels, xyz.device)
-        pyr.clear()
-        ops.raster_project(pyr, xyz, total_m)
         layout = L.FEAT_NHWC_BF16 if eng.bf16 else L.FEAT_NHWC_F32
         tex = texture.point_major()
-        for l in range(4):
-            ops.gather_from_zbuf(tex, pyr, l, layout, texture.activation, out=eng.inputs[l])
+        if (not want_maps) and texture.activation == 'none' and ops.fused_resolve_supported(pyr, tex.shape[1]):
+            # 2 launches: project all points into level 0, then ONE kernel derives levels 1..3, gathers the four
+            # feature maps and leaves level 0 cleared for the next frame
+            if not getattr(pyr, "level0_clean", False):
+                pyr.clear()
+            ops.raster_project(pyr, xyz, total_m, derive=False)
+            ops.pyramid_resolve_gather(tex, pyr, eng.inputs, layout, reset_level0=True)
+            pyr.level0_clean = True
+        else:
+            pyr.clear()
+            pyr.level0_clean = False
+            ops.raster_project(pyr, xyz, total_m)
+            for l in range(4):
+                ops.gather_from_zbuf(tex, pyr, l, layout, texture.activation, out=eng.inputs[l])
         out = eng.run()
         if want_maps:
             return out, [ops.zbuf_resolve(pyr, l) for l in range(n_levels)]

@@ -32,7 +32,8 @@
 
 namespace rb {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;            // 4 role warps + 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_TW = 16, TC_TH = 8;          // 128-pixel M tile
 constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024;
@@ -91,10 +92,8 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < a.Cout; i += TC_THREADS) {
-        s_par[i] = a.bias_f[i];
-        s_par[a.Cout + i] = a.bias_m[i];
-        s_par[2 * a.Cout + i] = a.scale[i];
-        s_par[3 * a.Cout + i] = a.shift[i];
+        // one float4 per channel: {bias_f, bias_m, bn_scale, bn_shift} -> a single LDS.128 in the epilogue
+        reinterpret_cast<float4 *>(s_par)[i] = make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i]);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -109,7 +108,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4);   // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * i, TC_EPI_WARPS);   // one arrival per epilogue warp
         }
         mbar_init(bres, 1);
         mbar_fence_init();
@@ -209,11 +208,16 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             umma_commit(tfull0 + 8 * acc);
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (8 warps: 2 per TMEM lane quadrant, interleaved over 16-column chunks) =====
+        // Software pipelined: the TMEM load of chunk c+1 and the residual/FAM-multiplier loads of chunk c+1 are in
+        // flight while chunk c is computed; the first chunk's global loads are issued BEFORE waiting for the MMAs.
         const int q = warp & 3;
-        const int r = q * 32 + lane;             // accumulator row == pixel within the tile
+        const int sub = (warp - 4) >> 2;          // 0 or 1: which chunks of the tile this warp owns
+        const int r = q * 32 + lane;              // accumulator row == pixel within the tile
         const int py = r / TC_TW, px = r % TC_TW;
         const int half = a.n_tile >> 1;
+        const int nchunks = half >> 4;
+        const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
         uint32_t tile_it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
             const int nt = (int)(t % a.n_tiles);
@@ -224,30 +228,47 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int b = mt / a.tiles_y;
             const int x = tx * TC_TW + px, y = ty * TC_TH + py;
             const bool inside = (x < a.W) && (y < a.H);
-            const long long pix = ((long long)b * a.H + y) * a.W + x;
+            const long long pixo = (((long long)b * a.H + y) * a.W + x) * a.Cout + nt * half;
             const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
-            mbar_wait(tfull0 + 8 * acc, acc_ph);
-            tcgen05_fence_after();
             const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < half; c0 += 16) {
-                uint32_t rf[16], rm[16];
-                tmem_ld16(trow + (uint32_t)c0, rf);
-                tmem_ld16(trow + (uint32_t)(half + c0), rm);
+
+            // two statically named register buffers (A/B): runtime-indexed arrays would be demoted to local memory
+            uint4 resA[2], resB[2], mulA[2], mulB[2];
+            uint32_t rfA[16], rmA[16], rfB[16], rmB[16];
+            auto prefetch = [&](int c, uint4 (&res)[2], uint4 (&mul)[2]) {
+                if (inside && c < nchunks) {
+                    const long long o = pixo + c * 16;
+                    if (a.residual) {
+                        res[0] = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        res[1] = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                    }
+                    if (a.out2) {
+                        mul[0] = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        mul[1] = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
+                    }
+                }
+            };
+            // computes chunk c from (rf, rm, res, mul) while the loads of chunk c+2 go into (rfn, rmn, resn, muln)
+            auto stage = [&](int c, uint32_t (&rf)[16], uint32_t (&rm)[16], uint4 (&res)[2], uint4 (&mul)[2],
+                             uint32_t (&rfn)[16], uint32_t (&rmn)[16], uint4 (&resn)[2], uint4 (&muln)[2]) {
                 tmem_ld_wait();
-                const int co = nt * half + c0;
+                const int cn = c + 2;
+                if (cn < nchunks) {
+                    tmem_ld16(trow + (uint32_t)(cn * 16), rfn);
+                    tmem_ld16(trow + (uint32_t)(half + cn * 16), rmn);
+                }
+                prefetch(cn, resn, muln);
+                const int co = nt * half + c * 16;
                 float yv[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    yv[j] = gated_epilogue_fast(__uint_as_float(rf[j]) + s_par[co + j],
-                                                __uint_as_float(rm[j]) + s_par[a.Cout + co + j], a.elu,
-                                                s_par[2 * a.Cout + co + j], s_par[3 * a.Cout + co + j]);
+                    const float4 pp = par4[co + j];
+                    yv[j] = gated_epilogue_fast(__uint_as_float(rf[j]) + pp.x, __uint_as_float(rm[j]) + pp.y, a.elu, pp.z, pp.w);
                 }
                 if (inside) {
-                    const long long o = pix * a.Cout + co;
+                    const long long o = pixo + c * 16;
                     if (a.residual) {
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        const uint32_t rr[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float2 f = unpack_bf16x2(rr[j]);
@@ -262,9 +283,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     if (a.out2) {
-                        const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
-                        const uint4 m1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
-                        const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                        const uint32_t mm[8] = {mul[0].x, mul[0].y, mul[0].z, mul[0].w, mul[1].x, mul[1].y, mul[1].z, mul[1].w};
                         uint32_t p2[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -277,6 +296,17 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         o2[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
                     }
                 }
+            };
+            prefetch(sub, resA, mulA);
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tcgen05_fence_after();
+            if (sub < nchunks) {
+                tmem_ld16(trow + (uint32_t)(sub * 16), rfA);
+                tmem_ld16(trow + (uint32_t)(half + sub * 16), rmA);
+            }
+            for (int c = sub; c < nchunks; c += 4) {
+                stage(c, rfA, rmA, resA, mulA, rfB, rmB, resB, mulB);
+                if (c + 2 < nchunks) stage(c + 2, rfB, rmB, resB, mulB, rfA, rmA, resA, mulA);
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -25,11 +25,10 @@ proj, view = synth.camera_batch(W, H, [7])
 m = torch.from_numpy(synth.total_matrix(proj, view)).to(dev)
 pyr = ops.Pyramid(1, W, H, LEVELS, dev)
 pyr.clear()
-ops.raster_project(pyr, xyz, m)
 tex = torch.rand((N, 8), device=dev)
 eng = UNetEngine(synth.synth_state_dict(synth.SEED), 1, H, W, dev, precision="bf16", use_graph=False)
-for l in range(4):
-    ops.gather_from_zbuf(tex, pyr, l, L.FEAT_NHWC_BF16, out=eng.inputs[l])
+ops.raster_project(pyr, xyz, m, derive=False)
+ops.pyramid_resolve_gather(tex, pyr, eng.inputs, L.FEAT_NHWC_BF16, reset_level0=True)
 torch.cuda.synchronize()
 sp = L.stream_ptr()
 by_name = {ly.name: ly for ly in eng.layers}

@@ -72,3 +72,54 @@ def test_point_texture_module_forward_backward_vs_oracle(act):
     with torch.no_grad():
         got2 = tex(ids.to(dev()))                          # inference path: cached shadow + fused activation
     assert float((got2.cpu() - want.detach()).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("layout", [L.FEAT_NHWC_BF16, L.FEAT_NHWC_F32])
+def test_fused_pyramid_resolve_equals_separate_kernels(layout):
+    """derive + 4 gathers + clear in ONE kernel must give the same pyramid and the same feature maps, bit for bit."""
+    from gpu_util import scene_and_cams
+    W, H, B = 96, 64, 3
+    xyz, M = scene_and_cams(60_000, W, H, [0, 3, 8])
+    d = dev()
+    x, m = torch.from_numpy(xyz).to(d), torch.from_numpy(M).to(d)
+    nd = torch.rand(60_000, 8, device=d)
+    ref = ops.Pyramid(B, W, H, 4, d)
+    ref.clear()
+    ops.raster_project(ref, x, m)                                   # separate path (derive kernels)
+    want = [ops.gather_from_zbuf(nd, ref, l, layout) for l in range(4)]
+    pyr = ops.Pyramid(B, W, H, 4, d)
+    pyr.clear()
+    ops.raster_project(pyr, x, m, derive=False)
+    dt = torch.bfloat16 if layout == L.FEAT_NHWC_BF16 else torch.float32
+    outs = [torch.full((B, H >> l, W >> l, 8), float("nan"), dtype=dt, device=d) for l in range(4)]
+    ops.pyramid_resolve_gather(nd, pyr, outs, layout, reset_level0=False)
+    assert torch.equal(pyr.buf, ref.buf)
+    for l in range(4):
+        assert torch.equal(outs[l], want[l]), l
+    # view sub-range + reset: only view 1, level 0 of that view cleared afterwards
+    outs1 = [torch.empty((1, H >> l, W >> l, 8), dtype=dt, device=d) for l in range(4)]
+    ops.pyramid_resolve_gather(nd, pyr, outs1, layout, view0=1, nviews=1, reset_level0=True)
+    for l in range(4):
+        assert torch.equal(outs1[l][0], want[l][1])
+    lvl0 = pyr.level(0).view(B, H, W)
+    assert bool((lvl0[1] == 0x7FFFFFFFFFFFFFFF).all()) and torch.equal(lvl0[0], ref.level(0).view(B, H, W)[0])
+
+
+def test_fused_render_twice_is_stable(synth_sd=None):
+    """NetAndTexture.render keeps level 0 clean between frames: the same camera twice gives identical frames."""
+    from read_b200 import synth
+    from read_b200.unet import UNet
+    from read_b200.compose import NetAndTexture
+    from gpu_util import scene_and_cams
+    xyz, M = scene_and_cams(40_000, 64, 64, [1])
+    net = UNet()
+    net.load_state_dict(synth.synth_state_dict(synth.SEED), strict=True)
+    tex = PointTexture(8, 40_000, init_method='rand')
+    model = NetAndTexture(net, {0: tex}, 1)
+    model.load_textures(0)
+    model.cuda().eval()
+    x, m = torch.from_numpy(xyz).cuda(), torch.from_numpy(M).cuda()
+    a = model.render(x, m, 64, 64).clone()
+    b = model.render(x, m, 64, 64).clone()
+    c, maps = model.render(x, m, 64, 64, want_maps=True)         # non-fused path
+    assert torch.equal(a, b) and torch.equal(a, c)
