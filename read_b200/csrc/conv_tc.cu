@@ -70,6 +70,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 }
 
 // ------------------------------------------------------------------ the kernel
+// KS = filter size (1 or 3), KKN = UMMA K-steps per tap chunk (cin_blk / 16), RES = weights resident in smem.
+// Compile-time so the single-thread MMA issue loop is straight-line code: round-1 profiling showed that thread, not
+// the tensor pipe, bounded every layer (85 scalar instructions per filter tap with runtime loop bounds).
+template <int KS, int KKN, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
@@ -78,9 +82,9 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
 
-    const int ntaps = a.ksize * a.ksize;
+    constexpr int ntaps = KS * KS;
     const uint32_t b_region = smem_base + a.b_region_off;
-    const uint32_t b_region_bytes = a.b_resident ? (uint32_t)(ntaps * a.kchunks) * a.b_bytes : (uint32_t)a.b_stages * a.b_bytes;
+    const uint32_t b_region_bytes = RES ? (uint32_t)(ntaps * a.kchunks) * a.b_bytes : (uint32_t)a.b_stages * a.b_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + b_region_bytes);
     const uint32_t bar0 = s_u32(bars);
     const uint32_t afull0 = bar0 + 8 * BAR_AFULL, aempty0 = bar0 + 8 * BAR_AEMPTY;
@@ -125,12 +129,14 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        if (a.b_resident) {
-            const int nb = ntaps * a.kchunks;
+        if (RES) {
+            const int nb = KS * KS * a.kchunks;
             mbar_arrive_expect_tx(bres, (uint32_t)nb * a.b_bytes);
             for (int i = 0; i < nb; ++i) tma_load_2d(&tmB, bres, b_region + (uint32_t)i * a.b_bytes, 0, i * n_total);
         }
         uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+        uint32_t a_addr = smem_base, b_addr = b_region;
+        const int row_step = KS * a.kchunks * n_total;                 // +1 filter row in the packed weights
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int nt = (int)(t % a.n_tiles);
             int mt = (int)(t / a.n_tiles);
@@ -140,19 +146,22 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int b = mt / a.tiles_y;
             const int x0 = tx * TC_TW - a.pad, y0 = ty * TC_TH - a.pad;
             for (int kc = 0; kc < a.kchunks; ++kc) {
-                for (int kx = 0; kx < a.ksize; ++kx) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
                     mbar_wait(aempty0 + 8 * as, aph ^ 1u);
                     mbar_arrive_expect_tx(afull0 + 8 * as, a.a_bytes);
-                    tma_load_4d(&tmA, afull0 + 8 * as, smem_base + as * a.a_bytes, kc * a.cin_blk, x0 + kx, y0, b);
-                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; }
-                    if (!a.b_resident) {
-                        int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*ksize + kx
-                        const int row_step = a.ksize * a.kchunks * n_total;
-                        for (int ky = 0; ky < a.ksize; ++ky, row += row_step) {
+                    tma_load_4d(&tmA, afull0 + 8 * as, a_addr, kc * a.cin_blk, x0 + kx, y0, b);
+                    a_addr += a.a_bytes;
+                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_addr = smem_base; }
+                    if (!RES) {
+                        int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*KS + kx
+#pragma unroll
+                        for (int ky = 0; ky < KS; ++ky, row += row_step) {
                             mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
                             mbar_arrive_expect_tx(bfull0 + 8 * bs, a.b_bytes);
-                            tma_load_2d(&tmB, bfull0 + 8 * bs, b_region + bs * a.b_bytes, 0, row);
-                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; }
+                            tma_load_2d(&tmB, bfull0 + 8 * bs, b_addr, 0, row);
+                            b_addr += a.b_bytes;
+                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_addr = b_region; }
                         }
                     }
                 }
@@ -161,48 +170,54 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t layout_type = (a.cin_blk == 64) ? 2u : 4u;
-        const uint32_t row_bytes = (uint32_t)a.cin_blk * 2u;
-        const uint32_t sbo = 8u * row_bytes;                      // 8 rows = one swizzle atom
-        const uint64_t desc_hi = make_kmajor_desc(0, sbo, layout_type);
-        const uint32_t ky_step = (TC_TW * row_bytes) >> 4;        // one tile row of pixels, in 16-byte units
-        const int kk_n = a.cin_blk / 16;
-        if (a.b_resident) mbar_wait(bres, 0);
+        constexpr uint32_t row_bytes = KKN * 16u * 2u;                 // cin_blk bf16
+        constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
+        const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, 8u * row_bytes, layout_type) >> 32);
+        constexpr uint32_t lo_lbo = 1u << 16;                          // LBO field (ignored for swizzled K-major), kept = 1
+        constexpr uint32_t ky_step = (TC_TW * row_bytes) >> 4;         // one tile row of pixels, in 16-byte units
+        const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_bytes >> 4;
+        const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
+        const uint32_t tap16 = (uint32_t)a.kchunks * b16;              // resident weights: +1 tap
+        if (RES) mbar_wait(bres, 0);
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, tile_it = 0;
+        uint32_t a_lo = a_lo0, b_lo = b_lo0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
             const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256u;
-            uint32_t first = 0;                                   // 0 until the first MMA of this tile was issued
-            for (int kc = 0; kc < a.kchunks; ++kc) {
-                for (int kx = 0; kx < a.ksize; ++kx) {
+            uint32_t bkc = b_lo0;                                      // resident weights: chunk kc of tap 0
+            for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
                     mbar_wait(afull0 + 8 * as, aph);
                     tcgen05_fence_after();
-                    const uint64_t adesc0 = desc_hi | (uint64_t)(((smem_base + as * a.a_bytes) & 0x3FFFFu) >> 4);
-                    for (int ky = 0; ky < a.ksize; ++ky) {
-                        uint32_t baddr;
-                        if (a.b_resident) {
-                            baddr = b_region + (uint32_t)((ky * a.ksize + kx) * a.kchunks + kc) * a.b_bytes;
+#pragma unroll
+                    for (int ky = 0; ky < KS; ++ky) {
+                        uint32_t bl;
+                        if (RES) {
+                            bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
                         } else {
                             mbar_wait(bfull0 + 8 * bs, bph);
                             tcgen05_fence_after();
-                            baddr = b_region + bs * a.b_bytes;
+                            bl = b_lo;
                         }
-                        const uint64_t adesc = adesc0 + (uint64_t)(ky * ky_step);
-                        const uint64_t bdesc = desc_hi | (uint64_t)((baddr & 0x3FFFFu) >> 4);
-                        for (int kk = 0; kk < kk_n; ++kk) {
-                            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, first);
-                            first = 1u;
+                        const uint32_t al = a_lo + (uint32_t)ky * ky_step;
+#pragma unroll
+                        for (int kk = 0; kk < KKN; ++kk) {
+                            // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                            const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                            umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
                         }
-                        if (!a.b_resident) {
+                        if (!RES) {
                             umma_commit(bempty0 + 8 * bs);
-                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; }
+                            b_lo += b16;
+                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
                         }
                     }
                     umma_commit(aempty0 + 8 * as);
-                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; }
+                    a_lo += a16;
+                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_lo = a_lo0; }
                 }
             }
             umma_commit(tfull0 + 8 * acc);
@@ -491,10 +506,28 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     const TcArgs &a = p->args;
     const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
-    RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
-    gated_conv_tc_kernel<<<(unsigned)grid, TC_THREADS, p->smem_bytes, st>>>(p->tmA, p->tmB, a);
+#define RB_TC_LAUNCH(KS_, KKN_, RES_)                                                                                   \
+    do {                                                                                                                \
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)p->smem_bytes));                                                              \
+        gated_conv_tc_kernel<KS_, KKN_, RES_><<<(unsigned)grid, TC_THREADS, p->smem_bytes, st>>>(p->tmA, p->tmB, a);    \
+    } while (0)
+    const int kkn = a.cin_blk / 16;
+    if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true);
+    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false);
+    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true);
+    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false);
+    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true);
+    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false);
+    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true);
+    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false);
+    else {
+        set_error("tcgen05 conv: no kernel instance for k=%d cin_blk=%d", a.ksize, a.cin_blk);
+        return READ_ERR_UNSUPPORTED;
+    }
+#undef RB_TC_LAUNCH
     RB_LAUNCH_CHECK();
     return READ_OK;
 }

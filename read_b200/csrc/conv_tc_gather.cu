@@ -37,6 +37,15 @@ struct GSrc {
     int C, H, W, mode, shift, c_begin;   // shift = log2(resample factor)
 };
 
+// Per-source parameters the producers read from shared memory (dynamic indexing of the kernel-parameter constant bank
+// is slow).  Nearest resampling is one formula for identity / down / up: src = clamp((dst << shl) >> shr).
+struct __align__(16) SrcS {
+    const __nv_bfloat16 *ptr;
+    long long plane;           // H*W*C elements per image
+    int C, W, H, rs;           // rs = W*C (row stride in elements)
+    int shl, shr, bil, pad_;
+};
+
 struct GArgs {
     GSrc src[READ_MAX_SRC];
     int n_src;
@@ -101,6 +110,19 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     // per-(K block, 16-byte chunk) decode table, built once per CTA so the producers' hot loop has no division:
     // {source index (-1 = zero padding of K), ky, kx, channel offset inside the source}
     int4 *s_tab = reinterpret_cast<int4 *>(s_par + 4 * CP);
+    SrcS *s_src = reinterpret_cast<SrcS *>(s_tab + a.kblocks * 8);
+    if (threadIdx.x < READ_MAX_SRC) {
+        const GSrc &g = a.src[threadIdx.x < a.n_src ? threadIdx.x : 0];
+        SrcS v;
+        v.ptr = g.ptr;
+        v.plane = (long long)g.H * g.W * g.C;
+        v.C = g.C; v.W = g.W; v.H = g.H; v.rs = g.W * g.C;
+        v.shl = g.mode == READ_SRC_NEAREST_DOWN ? g.shift : 0;
+        v.shr = g.mode == READ_SRC_NEAREST_UP ? g.shift : 0;
+        v.bil = g.mode == READ_SRC_BILINEAR_UP4 ? 1 : 0;
+        v.pad_ = 0;
+        s_src[threadIdx.x] = v;
+    }
     for (int i = threadIdx.x; i < a.kblocks * 8; i += G_THREADS) {
         const int kel = i * 8;
         int4 e = make_int4(-1, 0, 0, 0);
@@ -163,7 +185,10 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         if (lane == 0) {
             // ===================== MMA issuer =====================
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t s = 0, ph = 0, tile_it = 0;
+            const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, 1024u, 2u) >> 32);
+            const uint32_t st16 = stage_bytes >> 4, ab16 = a.a_bytes >> 4;
+            const uint32_t lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+            uint32_t s = 0, ph = 0, tile_it = 0, lo = lo0;
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
                 const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
@@ -172,14 +197,13 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(full0 + 8 * s, ph);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_base + s * stage_bytes;
-                    const uint64_t adesc = make_kmajor_desc(sa, 1024u, 2u);
-                    const uint64_t bdesc = make_kmajor_desc(sa + a.a_bytes, 1024u, 2u);
 #pragma unroll
                     for (int kk = 0; kk < G_KBLK / 16; ++kk)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+                        umma_bf16_lohi(d_tmem, lo + 2u * kk, lo + ab16 + 2u * kk, desc_hi, idesc,
+                                       kk != 0 ? 1u : (kb != 0 ? 1u : 0u));
                     umma_commit(empty0 + 8 * s);
-                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+                    lo += st16;
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; lo = lo0; }
                 }
                 umma_commit(tfull0 + 8 * acc);
             }
@@ -207,29 +231,22 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t dst0 = smem_base + s * stage_bytes + dst_off;
                 const int4 e = s_tab[kb * 8 + j];
-                const GSrc &sv = a.src[e.x < 0 ? 0 : e.x];
+                const SrcS sv = s_src[e.x < 0 ? 0 : e.x];
                 const int ix = ixb + e.z;
-                const bool xvalid = (e.x >= 0) && colok && (ix >= 0) && (ix < a.Win);
+                const bool xvalid = (e.x >= 0) && colok && ((unsigned)ix < (unsigned)a.Win);
                 const int iy0 = iyb + e.y;
-                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.H * sv.W * sv.C + e.w;
-                if (sv.mode != READ_SRC_BILINEAR_UP4) {
-                    int sx = ix;
-                    if (sv.mode == READ_SRC_NEAREST_DOWN) sx = ix << sv.shift;
-                    else if (sv.mode == READ_SRC_NEAREST_UP) sx = ix >> sv.shift;
-                    sx = sx < sv.W ? sx : sv.W - 1;
-                    sx = sx < 0 ? 0 : sx;
-                    const __nv_bfloat16 *colp = sbase + (long long)sx * sv.C;
-                    const long long rowstride = (long long)sv.W * sv.C;
+                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.plane + e.w;
+                if (!sv.bil) {
+                    int sx = (ix << sv.shl) >> sv.shr;
+                    sx = min(max(sx, 0), sv.W - 1);
+                    const __nv_bfloat16 *colp = sbase + sx * sv.C;
+                    int iy = iy0;
 #pragma unroll
-                    for (int i = 0; i < G_TH; ++i) {
-                        const int iy = iy0 + i * a.stride;
-                        const bool valid = xvalid && (i < rows_ok) && (iy >= 0) && (iy < a.Hin);
-                        int sy = iy;
-                        if (sv.mode == READ_SRC_NEAREST_DOWN) sy = iy << sv.shift;
-                        else if (sv.mode == READ_SRC_NEAREST_UP) sy = iy >> sv.shift;
-                        sy = sy < sv.H ? sy : sv.H - 1;
-                        sy = sy < 0 ? 0 : sy;
-                        const __nv_bfloat16 *p = colp + sy * rowstride;
+                    for (int i = 0; i < G_TH; ++i, iy += a.stride) {
+                        const bool valid = xvalid && (i < rows_ok) && ((unsigned)iy < (unsigned)a.Hin);
+                        int sy = (iy << sv.shl) >> sv.shr;
+                        sy = min(max(sy, 0), sv.H - 1);
+                        const __nv_bfloat16 *p = colp + (long long)sy * sv.rs;
                         cp_async16(dst0 + (uint32_t)i * 2048u, valid ? (const void *)p : (const void *)sv.ptr, valid ? 16u : 0u);
                     }
                 } else {
@@ -508,7 +525,7 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     a.out = d.out; a.out_mode = d.out_mode;
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
-    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 16 * (size_t)g.kblocks * 8 + 64;
+    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 16 * (size_t)g.kblocks * 8 + sizeof(SrcS) * READ_MAX_SRC + 64;
     *out = p;
     return READ_OK;
 }

@@ -98,6 +98,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// tcgen05.mma with the two 64-bit smem descriptors passed as (lo, hi) halves: the hi half (SBO / version / swizzle) is
+// a loop constant, the lo half (address >> 4) is a 32-bit add per instruction.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // mbarrier arrives once all tcgen05.mma previously issued by this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
