@@ -190,6 +190,9 @@ int read_conv_plan_launch(const read_conv_plan *p, void *stream);
 int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC / _TCGEN05 / _TCGEN05_GATHER */
 void read_conv_plan_destroy(read_conv_plan *p);
 
+/* nn.Upsample(scale_factor=4, mode='bilinear') (unet.py:200), NHWC [B,h,w,C] -> [B,4h,4w,C], C % 8 == 0. */
+int read_upsample_bilinear4(const void *in, int act_dtype, int B, int h, int w, int C, void *out, void *stream);
+
 /* Layout converters at the net boundary. */
 int read_nchw_f32_to_nhwc(const float *in, int B, int C, int H, int W, int act_dtype, void *out, void *stream);
 int read_nhwc_to_nchw_f32(const void *in, int act_dtype, int B, int C, int H, int W, float *out, void *stream);

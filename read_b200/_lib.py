@@ -75,6 +75,7 @@ _SIGS = {
     "read_conv_plan_launch": (c_int, [c_vp, c_vp]),
     "read_conv_plan_impl": (c_int, [c_vp]),
     "read_conv_plan_destroy": (None, [c_vp]),
+    "read_upsample_bilinear4": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_nchw_f32_to_nhwc": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_nhwc_to_nchw_f32": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_launch_count": (c_i64, []),

@@ -266,6 +266,41 @@ __global__ void nhwc_to_nchw_kernel(const TI *__restrict__ in, int B, int C, int
     }
 }
 
+// Bilinear x4 upsample, align_corners=False (nn.Upsample(scale_factor=4, mode='bilinear'), unet.py:200), NHWC, 8 channels
+// per thread.  Used by the bf16 engine so the decoder's 1x1 merge convs gather plain (identity) sources.
+template <typename T>
+__global__ void upsample_bilinear4_kernel(const T *__restrict__ in, int B, int h, int w, int C, T *__restrict__ out)
+{
+    const int cg = C >> 3;
+    const int H = h * 4, W = w * 4;
+    const long long total = (long long)B * H * W * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * 8;
+        long long r = i / cg;
+        const int x = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float sy = 0.25f * ((float)y + 0.5f) - 0.5f, sx = 0.25f * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = (y0 < h - 1) ? 1 : 0, xp = (x0 < w - 1) ? 1 : 0;
+        const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        const T *p = in + (((long long)b * h + y0) * w + x0) * C + c;
+        float v00[8], v01[8], v10[8], v11[8];
+        Vec8<T>::load(p, v00);
+        Vec8<T>::load(p + (long long)xp * C, v01);
+        Vec8<T>::load(p + (long long)yp * w * C, v10);
+        Vec8<T>::load(p + ((long long)yp * w + xp) * C, v11);
+        T *o = out + (((long long)b * H + y) * W + x) * C + c;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            o[k] = from_f32<T>(hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]));
+    }
+}
+
 int generic_npad(int Cout) { return ((Cout + 31) / 32) * 64; }
 int generic_kpad(int K) { return ((K + GC_BK - 1) / GC_BK) * GC_BK; }
 
@@ -317,6 +352,22 @@ int read_pack_weights_generic(const float *wf, const float *wm, int Cout, int Ci
     long long blocks = (total + 255) / 256;
     if (blocks > 65535) blocks = 65535;
     pack_generic_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(wf, wm, Cout, Cin, k, Npad, Kpad, out);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+int read_upsample_bilinear4(const void *in, int act_dtype, int B, int h, int w, int C, void *out, void *stream)
+{
+    RB_CHECK_ARG(in && out && B >= 1 && h >= 1 && w >= 1 && C >= 8 && C % 8 == 0, "upsample: bad arguments");
+    RB_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "upsample: 16B alignment");
+    const long long total = (long long)B * h * 4 * w * 4 * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+    if (act_dtype == READ_ACT_F32)
+        upsample_bilinear4_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float *)in, B, h, w, C, (float *)out);
+    else
+        upsample_bilinear4_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)in, B, h, w, C, (__nv_bfloat16 *)out);
     RB_LAUNCH_CHECK();
     return READ_OK;
 }

@@ -44,7 +44,7 @@ constexpr int BAR_AFULL = 0, BAR_AEMPTY = 8, BAR_BFULL = 16, BAR_BEMPTY = 24, BA
               BAR_BRES = 36, BAR_TMEMPTR = 38, BAR_PARAMS = 40;
 
 struct TcArgs {
-    int B, H, W, Cin, Cout;
+    int B, H, W, Cin, Cout, cout_pad;     // cout_pad > Cout only for the final (Cout <= 8, NCHW f32) layer
     int ksize, pad;
     int cin_blk, kchunks;
     int n_tile, n_tiles;
@@ -55,6 +55,7 @@ struct TcArgs {
     const float *bias_f, *bias_m, *scale, *shift;
     const __nv_bfloat16 *residual;
     __nv_bfloat16 *out;
+    float *out_nchw;                      // final layer only
     __nv_bfloat16 *out2;
     const __nv_bfloat16 *out2_mul;
 };
@@ -95,9 +96,10 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < a.Cout; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < a.cout_pad; i += TC_THREADS) {
         // one float4 per channel: {bias_f, bias_m, bn_scale, bn_shift} -> a single LDS.128 in the epilogue
-        reinterpret_cast<float4 *>(s_par)[i] = make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i]);
+        reinterpret_cast<float4 *>(s_par)[i] = i < a.Cout ? make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i])
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -247,6 +249,31 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
             const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
 
+            if (half == 8) {
+                // final layer (unet.py:285: BasicConv(32 -> 3), Cout padded to 8): one 8-column chunk, NCHW fp32 output
+                mbar_wait(tfull0 + 8 * acc, acc_ph);
+                tcgen05_fence_after();
+                if (sub == 0) {
+                    uint32_t f8[8], m8[8];
+                    tmem_ld8(trow, f8);
+                    tmem_ld8(trow + 8u, m8);
+                    tmem_ld_wait();
+                    if (inside) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < a.Cout) {
+                                const float4 pp = par4[j];
+                                a.out_nchw[(((long long)b * a.Cout + j) * a.H + y) * a.W + x] =
+                                    gated_epilogue_fast(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, a.elu, pp.z, pp.w);
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                continue;
+            }
             // two statically named register buffers (A/B): runtime-indexed arrays would be demoted to local memory
             uint4 resA[2], resB[2], mulA[2], mulB[2];
             uint32_t rfA[16], rmA[16], rfB[16], rmB[16];
@@ -339,11 +366,11 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 // ------------------------------------------------------------------ weight packing
 // out[((tap*kchunks + kc) * n_total + n) * cin_blk + kk],  n -> (tile nt, f|m half, channel)
-__global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__restrict__ wm, int Cout, int Cin, int k,
-                               int cin_blk, int n_tile, __nv_bfloat16 *__restrict__ out)
+__global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__restrict__ wm, int Cout, int cout_pad, int Cin,
+                               int k, int cin_blk, int n_tile, __nv_bfloat16 *__restrict__ out)
 {
     const int kchunks = Cin / cin_blk;
-    const int n_total = 2 * Cout;
+    const int n_total = 2 * cout_pad;
     const int half = n_tile / 2;
     const long long total = (long long)k * k * kchunks * n_total * cin_blk;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -360,13 +387,13 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
         const int c = kc * cin_blk + kk;
         const int ky = tap / k, kx = tap % k;
         const float *w = is_m ? wm : wf;
-        out[i] = __float2bfloat16_rn(w[(((long long)co * Cin + c) * k + ky) * k + kx]);
+        out[i] = __float2bfloat16_rn(co < Cout ? w[(((long long)co * Cin + c) * k + ky) * k + kx] : 0.f);
     }
 }
 
 // ------------------------------------------------------------------ host side
 struct TcGeom {
-    int cin_blk, kchunks, n_tile, n_tiles;
+    int cin_blk, kchunks, n_tile, n_tiles, cout_pad;
 };
 static bool tc_geom(int Cin, int Cout, TcGeom *g)
 {
@@ -374,12 +401,14 @@ static bool tc_geom(int Cin, int Cout, TcGeom *g)
     if (Cin % 64 == 0) cin_blk = 64;
     else if (Cin % 32 == 0) cin_blk = 32;
     else return false;
-    if (Cout % 16 != 0) return false;
-    const int n_total = 2 * Cout;
+    int cout_pad = Cout;
+    if (Cout <= 8) cout_pad = 8;                 // final layer: N = 16 (f|m of 8 padded channels)
+    else if (Cout % 16 != 0) return false;
+    const int n_total = 2 * cout_pad;
     const int n_tile = n_total <= 256 ? n_total : 256;
     if (n_total % n_tile != 0) return false;
-    if ((n_tile / 2) % 16 != 0) return false;
-    if (g) *g = TcGeom{cin_blk, Cin / cin_blk, n_tile, n_total / n_tile};
+    if (cout_pad > 8 && (n_tile / 2) % 16 != 0) return false;
+    if (g) *g = TcGeom{cin_blk, Cin / cin_blk, n_tile, n_total / n_tile, cout_pad};
     return true;
 }
 
@@ -389,8 +418,12 @@ bool tc_supported(const read_conv_desc &d)
     if (d.n_src != 1 || d.src[0].mode != READ_SRC_IDENTITY || d.mul != nullptr) return false;
     if (d.stride != 1 || !(d.k == 3 || d.k == 1)) return false;
     if (d.pad != (d.k - 1) / 2) return false;
-    if (d.out_mode != READ_OUT_NHWC) return false;
     if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+    if (d.Cout <= 8) {
+        if (d.out_mode != READ_OUT_NCHW_F32 || d.residual || d.out2) return false;   // final layer only
+    } else if (d.out_mode != READ_OUT_NHWC) {
+        return false;
+    }
     return tc_geom(d.Cin, d.Cout, nullptr);
 }
 
@@ -453,7 +486,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         }
     }
     {   // weights: dims {cin_blk, taps * kchunks * n_total}
-        const cuuint64_t rows = (cuuint64_t)d.k * d.k * g.kchunks * 2 * d.Cout;
+        const cuuint64_t rows = (cuuint64_t)d.k * d.k * g.kchunks * 2 * g.cout_pad;
         cuuint64_t dims[2] = {(cuuint64_t)g.cin_blk, rows};
         cuuint64_t strides[1] = {(cuuint64_t)g.cin_blk * 2};
         cuuint32_t box[2] = {(cuuint32_t)g.cin_blk, (cuuint32_t)g.n_tile};
@@ -468,7 +501,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         }
     }
     TcArgs &a = p->args;
-    a.B = d.B; a.H = d.Hout; a.W = d.Wout; a.Cin = d.Cin; a.Cout = d.Cout;
+    a.B = d.B; a.H = d.Hout; a.W = d.Wout; a.Cin = d.Cin; a.Cout = d.Cout; a.cout_pad = g.cout_pad;
     a.ksize = d.k; a.pad = d.pad;
     a.cin_blk = g.cin_blk; a.kchunks = g.kchunks; a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
     a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
@@ -494,9 +527,10 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
     a.out = static_cast<__nv_bfloat16 *>(d.out);
+    a.out_nchw = static_cast<float *>(d.out);
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
-    p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + 8 * BAR_PARAMS + 16 * (size_t)d.Cout + 64;
+    p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + 8 * BAR_PARAMS + 16 * (size_t)g.cout_pad + 64;
     *out = p;
     return READ_OK;
 }
@@ -542,8 +576,9 @@ extern "C" {
 
 int64_t read_tc_weight_elems(int Cout, int Cin, int k)
 {
-    if (!tc_geom(Cin, Cout, nullptr)) return -1;
-    return (int64_t)k * k * Cin * 2 * Cout;
+    TcGeom g;
+    if (!tc_geom(Cin, Cout, &g)) return -1;
+    return (int64_t)k * k * Cin * 2 * g.cout_pad;
 }
 
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream)
@@ -551,10 +586,10 @@ int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, in
     TcGeom g;
     RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc: null pointer");
     RB_CHECK_ARG(tc_geom(Cin, Cout, &g), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
-    const long long total = (long long)k * k * Cin * 2 * Cout;
+    const long long total = (long long)k * k * Cin * 2 * g.cout_pad;
     long long blocks = (total + 255) / 256;
     if (blocks > 65535) blocks = 65535;
-    pack_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(wf, wm, Cout, Cin, k, g.cin_blk, g.n_tile,
+    pack_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(wf, wm, Cout, g.cout_pad, Cin, k, g.cin_blk, g.n_tile,
                                                                       (__nv_bfloat16 *)out_bf16);
     RB_LAUNCH_CHECK();
     return READ_OK;

@@ -58,7 +58,9 @@ def test_generic_packing_geometry():
     lib = _lib.load()
     assert lib.read_generic_npad(3) == 64 and lib.read_generic_npad(32) == 64 and lib.read_generic_npad(56) == 128
     assert lib.read_tc_weight_elems(32, 32, 3) == 9 * 32 * 64
-    assert lib.read_tc_weight_elems(3, 32, 3) == -1                   # not a tensor-core shape
+    assert lib.read_tc_weight_elems(3, 32, 3) == 9 * 32 * 16          # final layer: Cout padded to 8 (N = 16)
+    assert lib.read_tc_weight_elems(56, 32, 1) == -1                  # not a TMA-kernel shape (gather kernel takes it)
+    assert lib.read_tcg_weight_elems(56, 32, 1) == 64 * 112           # K padded to one 64-block, N = 2*56
 
 
 def test_conv_validation_errors_without_gpu():

@@ -178,6 +178,7 @@ TC_CASES = [
     ("C64 1x1", [(64, 8, 16, "id", 1)], 64, 1, True, {}),
     ("C32 -> 64 channels, FAM product output", [(32, 16, 16, "id", 1)], 64, 3, True, {"out2": True}),
     ("many tiles per CTA (persistence, phases wrap)", [(32, 200, 208, "id", 1)], 32, 3, True, {"residual": True}),
+    ("final layer 32->3, NCHW f32 output", [(32, 24, 40, "id", 1)], 3, 3, False, {"final": True}),
 ]
 
 
@@ -228,9 +229,12 @@ def test_tc_supported_predicate():
     d.k, d.stride, d.pad, d.out_mode = 3, 1, 1, L.OUT_NHWC
     d.Hin = d.Hout = 8
     d.Win = d.Wout = 8
-    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]:
+    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]   # (32,3) needs NCHW f32 output, see below:
         d.Cin, d.Cout = cin, cout
         assert lib.read_conv_tc_supported(ctypes.byref(d)) == ok, (cin, cout)
+    d.Cin, d.Cout, d.out_mode = 32, 3, L.OUT_NCHW_F32
+    assert lib.read_conv_tc_supported(ctypes.byref(d)) == 1            # final layer shape
     d.Cin = d.Cout = 32
+    d.out_mode = L.OUT_NHWC
     d.act_dtype = L.ACT_F32
     assert lib.read_conv_tc_supported(ctypes.byref(d)) == 0
