@@ -51,6 +51,11 @@ template <> struct Vec8<float> {
         const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
+    static __device__ __forceinline__ void store(float *p, const float *v)
+    {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
 };
 template <> struct Vec8<__nv_bfloat16> {
     static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v)
@@ -63,6 +68,13 @@ template <> struct Vec8<__nv_bfloat16> {
             v[2 * i] = f.x;
             v[2 * i + 1] = f.y;
         }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v)
+    {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<uint4 *>(h);
     }
 };
 
@@ -295,9 +307,10 @@ __global__ void upsample_bilinear4_kernel(const T *__restrict__ in, int B, int h
         Vec8<T>::load(p + (long long)yp * w * C, v10);
         Vec8<T>::load(p + ((long long)yp * w + xp) * C, v11);
         T *o = out + (((long long)b * H + y) * W + x) * C + c;
+        float r[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            o[k] = from_f32<T>(hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]));
+        for (int k = 0; k < 8; ++k) r[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
+        Vec8<T>::store(o, r);
     }
 }
 

@@ -74,8 +74,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 // KS = filter size (1 or 3), KKN = UMMA K-steps per tap chunk (cin_blk / 16), RES = weights resident in smem.
 // Compile-time so the single-thread MMA issue loop is straight-line code: round-1 profiling showed that thread, not
 // the tensor pipe, bounded every layer (85 scalar instructions per filter tap with runtime loop bounds).
-template <int KS, int KKN, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NTHR = 384: 8 epilogue warps, 16-column chunks, software-pipelined (wide layers, Cout >= 128).
+// NTHR = 640: 16 epilogue warps, 8-column chunks (Cout <= 64): those layers have so little MMA work per tile (576 / 2304
+//             tensor cycles) that the epilogue's instruction stream bounds them; twice the warps halve each warp's
+//             share and give the schedulers 4 warps per SMSP to hide the MUFU / TMEM / global-load latencies.
+template <int KS, int KKN, bool RES, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
 gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
 {
@@ -96,7 +100,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < a.cout_pad; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < a.cout_pad; i += NTHR) {
         // one float4 per channel: {bias_f, bias_m, bn_scale, bn_shift} -> a single LDS.128 in the epilogue
         reinterpret_cast<float4 *>(s_par)[i] = i < a.Cout ? make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i])
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -114,7 +118,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, TC_EPI_WARPS);   // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * i, (NTHR - 128) / 32);   // one arrival per epilogue warp
         }
         mbar_init(bres, 1);
         mbar_fence_init();
@@ -129,13 +133,14 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const long long total_tiles = (long long)m_tiles * a.n_tiles;
     const int n_total = a.n_tile * a.n_tiles;
 
-    if (warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
-        if (RES) {
+    if (warp == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        if (RES && elect_one()) {
             const int nb = KS * KS * a.kchunks;
             mbar_arrive_expect_tx(bres, (uint32_t)nb * a.b_bytes);
             for (int i = 0; i < nb; ++i) tma_load_2d(&tmB, bres, b_region + (uint32_t)i * a.b_bytes, 0, i * n_total);
         }
+        __syncwarp();
         uint32_t as = 0, aph = 0, bs = 0, bph = 0;
         uint32_t a_addr = smem_base, b_addr = b_region;
         const int row_step = KS * a.kchunks * n_total;                 // +1 filter row in the packed weights
@@ -151,8 +156,11 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
                     mbar_wait(aempty0 + 8 * as, aph ^ 1u);
-                    mbar_arrive_expect_tx(afull0 + 8 * as, a.a_bytes);
-                    tma_load_4d(&tmA, afull0 + 8 * as, a_addr, kc * a.cin_blk, x0 + kx, y0, b);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(afull0 + 8 * as, a.a_bytes);
+                        tma_load_4d(&tmA, afull0 + 8 * as, a_addr, kc * a.cin_blk, x0 + kx, y0, b);
+                    }
+                    __syncwarp();
                     a_addr += a.a_bytes;
                     if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_addr = smem_base; }
                     if (!RES) {
@@ -160,8 +168,11 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int ky = 0; ky < KS; ++ky, row += row_step) {
                             mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
-                            mbar_arrive_expect_tx(bfull0 + 8 * bs, a.b_bytes);
-                            tma_load_2d(&tmB, bfull0 + 8 * bs, b_addr, 0, row);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(bfull0 + 8 * bs, a.b_bytes);
+                                tma_load_2d(&tmB, bfull0 + 8 * bs, b_addr, 0, row);
+                            }
+                            __syncwarp();
                             b_addr += a.b_bytes;
                             if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_addr = b_region; }
                         }
@@ -169,8 +180,8 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t row_bytes = KKN * 16u * 2u;                 // cin_blk bf16
         constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
@@ -205,24 +216,29 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             bl = b_lo;
                         }
                         const uint32_t al = a_lo + (uint32_t)ky * ky_step;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < KKN; ++kk) {
-                            // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                            const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
-                            umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
+                            for (int kk = 0; kk < KKN; ++kk) {
+                                // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                                const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                                umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
+                            }
+                            if (!RES) umma_commit(bempty0 + 8 * bs);
                         }
+                        __syncwarp();
                         if (!RES) {
-                            umma_commit(bempty0 + 8 * bs);
                             b_lo += b16;
                             if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
                         }
                     }
-                    umma_commit(aempty0 + 8 * as);
+                    if (elect_one()) umma_commit(aempty0 + 8 * as);
+                    __syncwarp();
                     a_lo += a16;
                     if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_lo = a_lo0; }
                 }
             }
-            umma_commit(tfull0 + 8 * acc);
+            if (elect_one()) umma_commit(tfull0 + 8 * acc);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================== epilogue (8 warps: 2 per TMEM lane quadrant, interleaved over 16-column chunks) =====
@@ -266,6 +282,66 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 a.out_nchw[(((long long)b * a.Cout + j) * a.H + y) * a.W + x] =
                                     gated_epilogue_fast(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, a.elu, pp.z, pp.w);
                             }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                continue;
+            }
+            if (NTHR == 640) {
+                // lean 16-warp path: warp = (TMEM lane quadrant q, column group sub of 8 channels), chunks sub, sub+4, ...
+                const int nch8 = half >> 3;
+                uint4 res8 = make_uint4(0, 0, 0, 0), mul8 = make_uint4(0, 0, 0, 0);
+                if (inside && sub < nch8) {
+                    if (a.residual) res8 = __ldg(reinterpret_cast<const uint4 *>(a.residual + pixo + sub * 8));
+                    if (a.out2) mul8 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + pixo + sub * 8));
+                }
+                mbar_wait(tfull0 + 8 * acc, acc_ph);
+                tcgen05_fence_after();
+                for (int c = sub; c < nch8; c += 4) {
+                    uint32_t f8[8], m8[8];
+                    tmem_ld8(trow + (uint32_t)(c * 8), f8);
+                    tmem_ld8(trow + (uint32_t)(half + c * 8), m8);
+                    tmem_ld_wait();
+                    const int co = nt * half + c * 8;
+                    float yv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 pp = par4[co + j];
+                        yv[j] = gated_epilogue_fast(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, a.elu, pp.z, pp.w);
+                    }
+                    if (inside) {
+                        const long long o = pixo + c * 8;
+                        if (a.residual) {
+                            const uint32_t rr[4] = {res8.x, res8.y, res8.z, res8.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = unpack_bf16x2(rr[j]);
+                                yv[2 * j] += f.x;
+                                yv[2 * j + 1] += f.y;
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                        *reinterpret_cast<uint4 *>(a.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (a.out2) {
+                            const uint32_t mm[4] = {mul8.x, mul8.y, mul8.z, mul8.w};
+                            uint32_t p2[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
+                                const float2 mv = unpack_bf16x2(mm[j]);
+                                p2[j] = pack_bf16x2(ys.x * mv.x, ys.y * mv.y);
+                            }
+                            *reinterpret_cast<uint4 *>(a.out2 + o) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        }
+                        const int cn = c + 4;   // next chunk of this warp (Cout = 64): fetch its residual now
+                        if (cn < nch8) {
+                            if (a.residual) res8 = __ldg(reinterpret_cast<const uint4 *>(a.residual + pixo + cn * 8));
+                            if (a.out2) mul8 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + pixo + cn * 8));
                         }
                     }
                 }
@@ -544,10 +620,17 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     if (grid > total_tiles) grid = total_tiles;
 #define RB_TC_LAUNCH(KS_, KKN_, RES_)                                                                                   \
     do {                                                                                                                \
-        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)p->smem_bytes));                                                              \
-        gated_conv_tc_kernel<KS_, KKN_, RES_><<<(unsigned)grid, TC_THREADS, p->smem_bytes, st>>>(p->tmA, p->tmB, a);    \
+        if (lean) {                                                                                                     \
+            RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, 640>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));             \
+            gated_conv_tc_kernel<KS_, KKN_, RES_, 640><<<(unsigned)grid, 640, p->smem_bytes, st>>>(p->tmA, p->tmB, a);   \
+        } else {                                                                                                        \
+            RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, 384>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));             \
+            gated_conv_tc_kernel<KS_, KKN_, RES_, 384><<<(unsigned)grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, a);   \
+        }                                                                                                               \
     } while (0)
+    const bool lean = a.cout_pad >= 16 && (a.n_tile >> 1) <= 64;       // Cout 16..64: 16-warp epilogue
     const int kkn = a.cin_blk / 16;
     if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true);
     else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false);

@@ -7,6 +7,22 @@ namespace rb {
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  The single-issuer roles (TMA producer, MMA issuer) run their loops with the WHOLE
+// warp and elect only the issuing instructions: warp-uniform control flow lets ptxas keep ring counters and UMMA
+// descriptors in uniform registers instead of converting per-thread values with R2UR before every tcgen05.mma.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -40,7 +40,8 @@ class UNetEngine:
         self.base, self.num_res = base, num_res
         self.sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
                    if v.dtype.is_floating_point}
-        self.layers = []
+        self.layers = []         # the 99 gated convs
+        self.ops = []            # launch order: convs + auxiliary kernels (bilinear upsamples in bf16 mode)
         self._keep = []          # tensors the plans point into
         self.use_graph = use_graph
         self.graph = None
@@ -132,7 +133,22 @@ class UNetEngine:
         ly.name, ly.plan, ly.impl, ly.keep = prefix, plan, lib.read_conv_plan_impl(plan), keep
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
         self.layers.append(ly)
+        self.ops.append(ly)
         return (out, out2) if out2_mul is not None else out
+
+    def _merge_src(self, t):
+        """Decoder skip merge input: nn.Upsample(x4, bilinear) of ``t`` (unet.py:260,268,276).  In bf16 mode the upsample is a
+        separate bandwidth-bound kernel so that the 1x1 merge conv gathers plain sources with cp.async; in fp32 parity mode
+        it is fused into the conv's operand loader."""
+        if not self.bf16 or self.conv_impl == "generic":
+            return (t, "bil4", 4)
+        B, h, w, c = t.shape
+        out = torch.empty((B, 4 * h, 4 * w, c), dtype=self.adt, device=self.device)
+        op = _Layer()
+        op.name, op.plan, op.impl, op.flops = f"upsample4({h}x{w}x{c})", None, -1, 0
+        op.keep = [t, out, (t.data_ptr(), B, h, w, c, out.data_ptr())]
+        self.ops.append(op)
+        return (out, "id", 1)
 
     # ------------------------------------------------------------------ blocks (unet.py:11-117)
     def _res(self, prefix, x, c):
@@ -182,13 +198,13 @@ class UNetEngine:
         r3 = self._aff(2, [(res1, "down", 4), (res2, "down", 2), (res3, "id", 1), (z, "up", 2)], 4 * c)
         z = self._block("Decoder.0", z, 8 * c)
         t = self._conv("feat_extract.7", [(z, "id", 1)], 4 * c, 4, 2, True)
-        z = self._conv("Convs.0", [(t, "bil4", 4), (r3, "id", 1)], 4 * c, 1, 1, True)
+        z = self._conv("Convs.0", [self._merge_src(t), (r3, "id", 1)], 4 * c, 1, 1, True)
         z = self._block("Decoder.1", z, 4 * c)
         t = self._conv("feat_extract.3", [(z, "id", 1)], 2 * c, 4, 2, True)
-        z = self._conv("Convs.1", [(t, "bil4", 4), (r2, "id", 1)], 2 * c, 1, 1, True)
+        z = self._conv("Convs.1", [self._merge_src(t), (r2, "id", 1)], 2 * c, 1, 1, True)
         z = self._block("Decoder.2", z, 2 * c)
         t = self._conv("feat_extract.4", [(z, "id", 1)], c, 4, 2, True)
-        z = self._conv("Convs.2", [(t, "bil4", 4), (r1, "id", 1)], c, 1, 1, True)
+        z = self._conv("Convs.2", [self._merge_src(t), (r1, "id", 1)], c, 1, 1, True)
         z = self._block("Decoder.3", z, c)
         self.output = self._conv("feat_extract.5", [(z, "id", 1)], 3, 3, 1, False, final=True)
         self.flops = sum(l.flops for l in self.layers)
@@ -196,9 +212,17 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ execution
     def _launch_all(self):
-        lib, stream = self.lib, L.stream_ptr()
-        for ly in self.layers:
-            L.check(lib.read_conv_plan_launch(ly.plan, stream))
+        stream = L.stream_ptr()
+        for op in self.ops:
+            self.launch_op(op, stream)
+
+    def launch_op(self, op, stream=None):
+        stream = L.stream_ptr() if stream is None else stream
+        if op.plan is not None:
+            L.check(self.lib.read_conv_plan_launch(op.plan, stream))
+        else:
+            src, B, h, w, c, dst = op.keep[2]
+            L.check(self.lib.read_upsample_bilinear4(src, self.act_code, B, h, w, c, dst, stream))
 
     def run(self):
         """Run the net on whatever is in ``self.inputs``; result in ``self.output`` ([B,3,H,W] f32)."""
@@ -216,7 +240,7 @@ class UNetEngine:
         return self.output
 
     def n_launches(self):
-        return len(self.layers)
+        return len(self.ops)
 
     def impl_histogram(self):
         names = {L.CONV_GENERIC: "generic", L.CONV_TCGEN05: "tcgen05", L.CONV_TCGEN05_GATHER: "tcgen05_gather"}

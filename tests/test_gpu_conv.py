@@ -229,7 +229,7 @@ def test_tc_supported_predicate():
     d.k, d.stride, d.pad, d.out_mode = 3, 1, 1, L.OUT_NHWC
     d.Hin = d.Hout = 8
     d.Win = d.Wout = 8
-    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]   # (32,3) needs NCHW f32 output, see below:
+    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]:   # (32,3) needs NCHW f32 output, see below
         d.Cin, d.Cout = cin, cout
         assert lib.read_conv_tc_supported(ctypes.byref(d)) == ok, (cin, cout)
     d.Cin, d.Cout, d.out_mode = 32, 3, L.OUT_NCHW_F32
@@ -238,3 +238,20 @@ def test_tc_supported_predicate():
     d.out_mode = L.OUT_NHWC
     d.act_dtype = L.ACT_F32
     assert lib.read_conv_tc_supported(ctypes.byref(d)) == 0
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_upsample_bilinear4_matches_torch(bf16):
+    lib = L.load()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand((2, 16, 5, 7), generator=g)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    if bf16:
+        x = x.to(dt).float()
+    want = F.interpolate(x, scale_factor=4, mode="bilinear", align_corners=False)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(dev(), dt)
+    out = torch.empty((2, 20, 28, 16), dtype=dt, device=dev())
+    L.check(lib.read_upsample_bilinear4(xin.data_ptr(), L.ACT_BF16 if bf16 else L.ACT_F32, 2, 5, 7, 16, out.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    err = float((out.float().permute(0, 3, 1, 2).cpu() - want).abs().max())
+    assert err < (2 ** -8 if bf16 else 1e-6), err
