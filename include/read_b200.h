@@ -37,6 +37,9 @@ enum {
 
 int read_version(void);
 const char *read_last_error(void);
+/* Tuning / debugging knobs (results are identical for every setting): "raster_pipelined" (default 1),
+ * "raster_bulk_tma" (default 1). */
+int read_set_option(const char *name, int value);
 /* 1 if the current device is sm_100 (B200); the library refuses to launch elsewhere. */
 int read_device_ok(void);
 

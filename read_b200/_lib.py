@@ -46,6 +46,7 @@ _SIGS = {
     "read_version": (c_int, []),
     "read_last_error": (ctypes.c_char_p, []),
     "read_device_ok": (c_int, []),
+    "read_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "read_pyramid_entries": (c_i64, [c_int, c_int, c_int, c_int]),
     "read_pyramid_level_offset": (c_i64, [c_int, c_int, c_int, c_int]),
     "read_level_size": (None, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

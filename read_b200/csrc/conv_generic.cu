@@ -307,10 +307,10 @@ __global__ void upsample_bilinear4_kernel(const T *__restrict__ in, int B, int h
         Vec8<T>::load(p + (long long)yp * w * C, v10);
         Vec8<T>::load(p + ((long long)yp * w + xp) * C, v11);
         T *o = out + (((long long)b * H + y) * W + x) * C + c;
-        float r[8];
+        float res[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
-        Vec8<T>::store(o, r);
+        for (int k = 0; k < 8; ++k) res[k] = hy * (hx * v00[k] + lx * v01[k]) + ly * (hx * v10[k] + lx * v11[k]);
+        Vec8<T>::store(o, res);
     }
 }
 
