@@ -25,6 +25,21 @@ __device__ __forceinline__ float gated_epilogue_fast(float f, float m, int elu, 
     return fmaf(a * s, scale, shift);
 }
 
+// Same, activation chosen at compile time (the no-activation layers never touch the ex2 pipe).
+template <bool ELU>
+__device__ __forceinline__ float gate_fast(float f, float m, float scale, float shift)
+{
+    float a = f;
+    if (ELU) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f * 1.4426950408889634f));
+        a = f <= 0.f ? (e - 1.f) : f;
+    }
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * m));
+    return fmaf(a * fmaf(0.5f, th, 0.5f), scale, shift);
+}
+
 int generic_npad(int Cout);
 int generic_kpad(int K);
 int launch_generic(const read_conv_desc &d, cudaStream_t st);

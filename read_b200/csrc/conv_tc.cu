@@ -20,9 +20,9 @@
 //   epilogue    tcgen05.ld -> bias, ELU, sigmoid gate, BN affine, residual add, bf16 pack -> global
 //               (optionally a second output y*z for the following FAM, unet.py:115).
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
-// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quadrant = warp%4).  The two single-thread roles keep
-// their ring indices/phases incrementally: no integer division on the per-k-step path.
+// Warp roles (384 or 640 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warps 1 and 3 = MMA issuers
+// (alternate tiles), warp2 = TMEM allocator, warps 4.. = epilogue (TMEM lane quadrant = warp%4).  The issuing roles
+// keep their ring indices/phases incrementally: no integer division on the per-k-step path.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "ptx.cuh"
@@ -35,13 +35,13 @@ namespace rb {
 constexpr int TC_THREADS = 384;            // 4 role warps + 8 epilogue warps
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_TW = 16, TC_TH = 8;          // 128-pixel M tile
-constexpr int TC_MAX_STAGES = 8;
-constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_MAX_STAGES = 16;           // ring depth bounds the bytes in flight per SM (latency-bound small-C layers)
+constexpr uint32_t TC_SMEM_BUDGET = 218 * 1024;
 constexpr uint32_t TC_RESIDENT_MAX = 144 * 1024;
 constexpr int TC_TMEM_COLS = 512;
 // barrier slots (uint64 each)
-constexpr int BAR_AFULL = 0, BAR_AEMPTY = 8, BAR_BFULL = 16, BAR_BEMPTY = 24, BAR_TFULL = 32, BAR_TEMPTY = 34,
-              BAR_BRES = 36, BAR_TMEMPTR = 38, BAR_PARAMS = 40;
+constexpr int BAR_AFULL = 0, BAR_AEMPTY = 16, BAR_BFULL = 32, BAR_BEMPTY = 48, BAR_TFULL = 64, BAR_TEMPTY = 66,
+              BAR_BRES = 68, BAR_TMEMPTR = 70, BAR_PARAMS = 72;
 
 struct TcArgs {
     int B, H, W, Cin, Cout, cout_pad;     // cout_pad > Cout only for the final (Cout <= 8, NCHW f32) layer
@@ -50,6 +50,8 @@ struct TcArgs {
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
     int a_stages, b_stages, b_resident;
+    float inv_tx, inv_ty;                  // 1/tiles_x, 1/tiles_y for the division-free tile decode
+    int dual;                              // two MMA issuer warps, each with its own half of the A ring (resident weights only)
     uint32_t a_bytes, b_bytes, b_region_off;   // halo tile bytes, one weight tile bytes, byte offset of the B region
     int elu;
     const float *bias_f, *bias_m, *scale, *shift;
@@ -59,6 +61,28 @@ struct TcArgs {
     __nv_bfloat16 *out2;
     const __nv_bfloat16 *out2_mul;
 };
+
+// tile index -> (n tile, tile x, tile y, image) without integer division (a runtime IDIV costs ~20 instructions and
+// every warp of every role decodes every tile).  floor((x + 0.5) * (1/d)) is exact for the x < 2^22 we ever see:
+// the fractional part of (x+0.5)/d is at least 0.5/d away from an integer, far more than the fp32 rounding error.
+__device__ __forceinline__ int fdiv_small(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
+
+struct TileCoord {
+    int nt, tx, ty, b;
+};
+__device__ __forceinline__ TileCoord decode_tile(long long t, const TcArgs &a)
+{
+    TileCoord c;
+    int mt = (int)t;
+    c.nt = 0;
+    if (a.n_tiles == 2) { c.nt = mt & 1; mt >>= 1; }
+    else if (a.n_tiles > 2) { c.nt = (int)(t % a.n_tiles); mt = (int)(t / a.n_tiles); }
+    const int q = fdiv_small(mt, a.inv_tx);
+    c.tx = mt - q * a.tiles_x;
+    c.b = fdiv_small(q, a.inv_ty);
+    c.ty = q - c.b * a.tiles_y;
+    return c;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 {
@@ -141,28 +165,41 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int i = 0; i < nb; ++i) tma_load_2d(&tmB, bres, b_region + (uint32_t)i * a.b_bytes, 0, i * n_total);
         }
         __syncwarp();
-        uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-        uint32_t a_addr = smem_base, b_addr = b_region;
+        // A ring(s): one ring, or (dual issuers) two half rings used by alternate tiles - each ring is then a plain
+        // single-producer / single-consumer queue, so mbarrier phase parity can never alias
+        const uint32_t ring_n = a.dual ? (uint32_t)a.a_stages / 2u : (uint32_t)a.a_stages;
+        uint32_t as_[2] = {0u, 0u}, aph_[2] = {0u, 0u};
+        uint32_t bs = 0, bph = 0, tile_it = 0;
+        uint32_t b_addr = b_region;
         const int row_step = KS * a.kchunks * n_total;                 // +1 filter row in the packed weights
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int nt = (int)(t % a.n_tiles);
-            int mt = (int)(t / a.n_tiles);
-            const int tx = mt % a.tiles_x;
-            mt /= a.tiles_x;
-            const int ty = mt % a.tiles_y;
-            const int b = mt / a.tiles_y;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const uint32_t ring = a.dual ? (tile_it & 1u) : 0u;
+            uint32_t as = ring ? as_[1] : as_[0], aph = ring ? aph_[1] : aph_[0];
+            const uint32_t ring_base = ring * ring_n;
+            const TileCoord tc_ = decode_tile(t, a);
+            const int nt = tc_.nt, tx = tc_.tx, ty = tc_.ty, b = tc_.b;
             const int x0 = tx * TC_TW - a.pad, y0 = ty * TC_TH - a.pad;
+            // warm L2 with the halo tile this CTA will need two tiles from now (DRAM latency is what bounds the small-C
+            // layers: the ring can only keep a_stages * a_bytes in flight per SM)
+            const long long tp = t + 2 * (long long)gridDim.x;
+            if (tp < total_tiles && elect_one()) {
+                const TileCoord pc = decode_tile(tp, a);
+                const int ptx_ = pc.tx, pty = pc.ty, pb = pc.b;
+                for (int kc = 0; kc < a.kchunks; ++kc)
+                    tma_prefetch_4d(&tmA, kc * a.cin_blk, ptx_ * TC_TW, pty * TC_TH - a.pad, pb);
+            }
+            __syncwarp();
             for (int kc = 0; kc < a.kchunks; ++kc) {
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
-                    mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+                    const uint32_t slot = ring_base + as;
+                    mbar_wait(aempty0 + 8 * slot, aph ^ 1u);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(afull0 + 8 * as, a.a_bytes);
-                        tma_load_4d(&tmA, afull0 + 8 * as, a_addr, kc * a.cin_blk, x0 + kx, y0, b);
+                        mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_bytes);
+                        tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0 + kx, y0, b);
                     }
                     __syncwarp();
-                    a_addr += a.a_bytes;
-                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_addr = smem_base; }
+                    if (++as == ring_n) { as = 0; aph ^= 1u; }
                     if (!RES) {
                         int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*KS + kx
 #pragma unroll
@@ -179,9 +216,15 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
             }
+            if (ring) { as_[1] = as; aph_[1] = aph; } else { as_[0] = as; aph_[0] = aph; }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    } else if (warp == 1 || warp == 3) {
+        // ===================== MMA issuers (whole warp loops, one elected lane issues) =====================
+        // TWO issuer warps take alternate tiles (accumulator 0 / 1): every tcgen05.mma costs its issuing thread ~10 scalar
+        // instructions (~100+ cycles for a lone warp) - more than the 8..64 tensor cycles of the small-N layers' MMAs - so
+        // two independent instruction streams into the tensor pipe nearly double its occupancy.  A/B ring stages are
+        // produced in tile order; each issuer consumes its own tiles' stages and skips over the other issuer's.
+        const uint32_t me = (warp == 3) ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t row_bytes = KKN * 16u * 2u;                 // cin_blk bf16
         constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
@@ -194,7 +237,12 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (RES) mbar_wait(bres, 0);
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, tile_it = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0;
+        const uint32_t ring_n = a.dual ? (uint32_t)a.a_stages / 2u : (uint32_t)a.a_stages;
+        const uint32_t ring_lo0 = a_lo0 + (a.dual ? me * ring_n * a16 : 0u);
+        const uint32_t ring_bar = a.dual ? me * ring_n : 0u;
+        a_lo = ring_lo0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            if (a.dual ? ((tile_it & 1u) != me) : (me != 0u)) continue;   // not this issuer's tile
             const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
             tcgen05_fence_after();
@@ -203,7 +251,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
-                    mbar_wait(afull0 + 8 * as, aph);
+                    mbar_wait(afull0 + 8 * (ring_bar + as), aph);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
@@ -231,10 +279,10 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
                         }
                     }
-                    if (elect_one()) umma_commit(aempty0 + 8 * as);
+                    if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
                     __syncwarp();
                     a_lo += a16;
-                    if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1u; a_lo = a_lo0; }
+                    if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
                 }
             }
             if (elect_one()) umma_commit(tfull0 + 8 * acc);
@@ -253,12 +301,8 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
         uint32_t tile_it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-            const int nt = (int)(t % a.n_tiles);
-            int mt = (int)(t / a.n_tiles);
-            const int tx = mt % a.tiles_x;
-            mt /= a.tiles_x;
-            const int ty = mt % a.tiles_y;
-            const int b = mt / a.tiles_y;
+            const TileCoord tc_ = decode_tile(t, a);
+            const int nt = tc_.nt, tx = tc_.tx, ty = tc_.ty, b = tc_.b;
             const int x = tx * TC_TW + px, y = ty * TC_TH + py;
             const bool inside = (x < a.W) && (y < a.H);
             const long long pixo = (((long long)b * a.H + y) * a.W + x) * a.Cout + nt * half;
@@ -307,10 +351,18 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     tmem_ld_wait();
                     const int co = nt * half + c * 8;
                     float yv[8];
+                    if (a.elu) {            // warp-uniform: the no-activation layers skip the ex2 path entirely
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 pp = par4[co + j];
-                        yv[j] = gated_epilogue_fast(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, a.elu, pp.z, pp.w);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 pp = par4[co + j];
+                            yv[j] = gate_fast<true>(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, pp.z, pp.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 pp = par4[co + j];
+                            yv[j] = gate_fast<false>(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, pp.z, pp.w);
+                        }
                     }
                     if (inside) {
                         const long long o = pixo + c * 8;
@@ -378,10 +430,18 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 prefetch(cn, resn, muln);
                 const int co = nt * half + c * 16;
                 float yv[16];
+                if (a.elu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 pp = par4[co + j];
-                    yv[j] = gated_epilogue_fast(__uint_as_float(rf[j]) + pp.x, __uint_as_float(rm[j]) + pp.y, a.elu, pp.z, pp.w);
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 pp = par4[co + j];
+                        yv[j] = gate_fast<true>(__uint_as_float(rf[j]) + pp.x, __uint_as_float(rm[j]) + pp.y, pp.z, pp.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 pp = par4[co + j];
+                        yv[j] = gate_fast<false>(__uint_as_float(rf[j]) + pp.x, __uint_as_float(rm[j]) + pp.y, pp.z, pp.w);
+                    }
                 }
                 if (inside) {
                     const long long o = pixo + c * 16;
@@ -598,6 +658,10 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         a.b_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         b_region_bytes = (uint32_t)a.b_stages * a.b_bytes;
     }
+    a.inv_tx = 1.0f / (float)a.tiles_x;
+    a.inv_ty = 1.0f / (float)a.tiles_y;
+    a.dual = (a.b_resident && a.a_stages >= 6) ? 1 : 0;
+    if (a.dual) a.a_stages &= ~1;            // two equal half rings
     a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;

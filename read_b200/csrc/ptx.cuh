@@ -59,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 
@@ -84,6 +84,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint32_t bar,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): warms L2 for a tile that will be loaded later
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
 {
