@@ -40,6 +40,29 @@ __device__ __forceinline__ float gate_fast(float f, float m, float scale, float 
     return fmaf(a * fmaf(0.5f, th, 0.5f), scale, shift);
 }
 
+// Same tail with the constants pre-folded by the caller: p = {bias_f, bias_m / 2, bn_scale / 2, bn_shift}.
+//   sigmoid(m + b_m) = (1 + tanh(m/2 + b_m/2)) / 2   =>   y = a * (1 + th) * (scale / 2) + shift
+// 9 instructions per output with ELU (FADD, FFMA, FMUL, 2 MUFU, FSETP, FADD, 2 FFMA), 5 without.
+template <bool ELU>
+__device__ __forceinline__ float gate_folded(float f, float m, const float4 p)
+{
+    const float v = f + p.x;
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(m, 0.5f, p.y)));
+    float a = v;
+    if (ELU) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+        a = v <= 0.f ? (e - 1.f) : v;
+    }
+    return fmaf(fmaf(a, th, a), p.z, p.w);
+}
+
+// floor(x / d) without integer division (a runtime IDIV costs ~20 instructions and every warp of every role decodes
+// every tile).  floor((x + 0.5) * (1/d)) is exact for the x < 2^22 we ever see: the fractional part of (x+0.5)/d is at
+// least 0.5/d away from an integer, far more than the fp32 rounding error.
+__device__ __forceinline__ int fdiv_small(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
+
 int generic_npad(int Cout);
 int generic_kpad(int K);
 int launch_generic(const read_conv_desc &d, cudaStream_t st);

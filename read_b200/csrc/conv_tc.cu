@@ -40,8 +40,9 @@ constexpr uint32_t TC_SMEM_BUDGET = 218 * 1024;
 constexpr uint32_t TC_RESIDENT_MAX = 144 * 1024;
 constexpr int TC_TMEM_COLS = 512;
 // barrier slots (uint64 each)
-constexpr int BAR_AFULL = 0, BAR_AEMPTY = 16, BAR_BFULL = 32, BAR_BEMPTY = 48, BAR_TFULL = 64, BAR_TEMPTY = 66,
-              BAR_BRES = 68, BAR_TMEMPTR = 70, BAR_PARAMS = 72;
+constexpr int TC_MAX_ACC = 8;               // TMEM accumulator ring: 512 columns / n_tile, at most 8
+constexpr int BAR_AFULL = 0, BAR_AEMPTY = 16, BAR_BFULL = 32, BAR_BEMPTY = 48, BAR_TFULL = 64, BAR_TEMPTY = 72,
+              BAR_BRES = 80, BAR_TMEMPTR = 82, BAR_PARAMS = 84;
 
 struct TcArgs {
     int B, H, W, Cin, Cout, cout_pad;     // cout_pad > Cout only for the final (Cout <= 8, NCHW f32) layer
@@ -50,8 +51,13 @@ struct TcArgs {
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
     int a_stages, b_stages, b_resident;
+    int kxs;                               // filter columns per A ring stage (1, or ksize: tile-granular stages)
     float inv_tx, inv_ty;                  // 1/tiles_x, 1/tiles_y for the division-free tile decode
+    int nacc;                              // accumulator ring depth (each n_tile TMEM columns wide)
     int dual;                              // two MMA issuer warps, each with its own half of the A ring (resident weights only)
+    int debug;                             // diagnostic knobs (read_set_option "tc_debug"): 1 = lean epilogue only hand-shakes,
+                                           // 2 = issuers skip the MMAs, 4 = producer skips the A loads, 8 = lean epilogue
+                                           // computes but does not touch global memory, 16 = single MMA issuer
     uint32_t a_bytes, b_bytes, b_region_off;   // halo tile bytes, one weight tile bytes, byte offset of the B region
     int elu;
     const float *bias_f, *bias_m, *scale, *shift;
@@ -62,11 +68,7 @@ struct TcArgs {
     const __nv_bfloat16 *out2_mul;
 };
 
-// tile index -> (n tile, tile x, tile y, image) without integer division (a runtime IDIV costs ~20 instructions and
-// every warp of every role decodes every tile).  floor((x + 0.5) * (1/d)) is exact for the x < 2^22 we ever see:
-// the fractional part of (x+0.5)/d is at least 0.5/d away from an integer, far more than the fp32 rounding error.
-__device__ __forceinline__ int fdiv_small(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
-
+// tile index -> (n tile, tile x, tile y, image) without integer division: fdiv_small, conv_common.cuh
 struct TileCoord {
     int nt, tx, ty, b;
 };
@@ -89,6 +91,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+// one F2FP per pair: lo -> bits [0,16) (lower address), hi -> bits [16,32)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u));
@@ -102,7 +111,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 // NTHR = 640: 16 epilogue warps, 8-column chunks (Cout <= 64): those layers have so little MMA work per tile (576 / 2304
 //             tensor cycles) that the epilogue's instruction stream bounds them; twice the warps halve each warp's
 //             share and give the schedulers 4 warps per SMSP to hide the MUFU / TMEM / global-load latencies.
-template <int KS, int KKN, bool RES, int NTHR>
+// KXS = filter columns per A ring stage: 1, or KS (one stage = the whole tile's k halo loads; needs resident weights).
+//       Round-1 knob experiments: with ALL work disabled the C=32 kernel still took 1600 cycles per tile - the serial
+//       latency of one producer warp doing 3 x (wait, expect_tx, TMA, ring update) per tile and of the issuers' per-stage
+//       wait / elect / commit.  A tile-granular stage needs one wait, one expect_tx and one commit per tile.
+template <int KS, int KKN, bool RES, int NTHR, int EPI, int KXS>
 __global__ void __launch_bounds__(NTHR, 1)
 gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
@@ -126,7 +139,9 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     for (int i = threadIdx.x; i < a.cout_pad; i += NTHR) {
         // one float4 per channel: {bias_f, bias_m, bn_scale, bn_shift} -> a single LDS.128 in the epilogue
-        reinterpret_cast<float4 *>(s_par)[i] = i < a.Cout ? make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i])
+        // (the lean path stores them pre-folded for gate_folded: {bias_f, bias_m / 2, bn_scale / 2, bn_shift})
+        const float hs = NTHR == 640 ? 0.5f : 1.f;
+        reinterpret_cast<float4 *>(s_par)[i] = i < a.Cout ? make_float4(a.bias_f[i], hs * a.bias_m[i], hs * a.scale[i], a.shift[i])
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 0 && lane == 0) {
@@ -140,9 +155,9 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(bfull0 + 8 * s, 1);
             mbar_init(bempty0 + 8 * s, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TC_MAX_ACC; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, (NTHR - 128) / 32);   // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * i, NTHR == 640 ? (uint32_t)(a.n_tile >> 3) : (NTHR - 128) / 32);   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
         }
         mbar_init(bres, 1);
         mbar_fence_init();
@@ -157,9 +172,11 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const long long total_tiles = (long long)m_tiles * a.n_tiles;
     const int n_total = a.n_tile * a.n_tiles;
 
-    if (warp == 0) {
-        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
-        if (RES && elect_one()) {
+    if (warp == 0 || (warp == 2 && a.dual)) {
+        // ===================== TMA producer(s) (whole warp loops, one elected lane issues) =====================
+        // With dual issuers there are two producers as well: warp 0 feeds ring 0 (even tiles), warp 2 ring 1 (odd tiles).
+        const uint32_t pme = (warp == 2) ? 1u : 0u;
+        if (RES && pme == 0u && elect_one()) {
             const int nb = KS * KS * a.kchunks;
             mbar_arrive_expect_tx(bres, (uint32_t)nb * a.b_bytes);
             for (int i = 0; i < nb; ++i) tma_load_2d(&tmB, bres, b_region + (uint32_t)i * a.b_bytes, 0, i * n_total);
@@ -168,20 +185,21 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // A ring(s): one ring, or (dual issuers) two half rings used by alternate tiles - each ring is then a plain
         // single-producer / single-consumer queue, so mbarrier phase parity can never alias
         const uint32_t ring_n = a.dual ? (uint32_t)a.a_stages / 2u : (uint32_t)a.a_stages;
-        uint32_t as_[2] = {0u, 0u}, aph_[2] = {0u, 0u};
+        const uint32_t ring_base = a.dual ? pme * ring_n : 0u;
+        const uint32_t stage_bytes = (uint32_t)KXS * a.a_bytes;
+        uint32_t as = 0, aph = 0;
         uint32_t bs = 0, bph = 0, tile_it = 0;
         uint32_t b_addr = b_region;
         const int row_step = KS * a.kchunks * n_total;                 // +1 filter row in the packed weights
+        const long long pf_dist = (a.dual ? 4 : 2) * (long long)gridDim.x;   // this producer's tile after next
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-            const uint32_t ring = a.dual ? (tile_it & 1u) : 0u;
-            uint32_t as = ring ? as_[1] : as_[0], aph = ring ? aph_[1] : aph_[0];
-            const uint32_t ring_base = ring * ring_n;
+            if (a.dual && (tile_it & 1u) != pme) continue;             // the other producer's tile
             const TileCoord tc_ = decode_tile(t, a);
             const int nt = tc_.nt, tx = tc_.tx, ty = tc_.ty, b = tc_.b;
             const int x0 = tx * TC_TW - a.pad, y0 = ty * TC_TH - a.pad;
-            // warm L2 with the halo tile this CTA will need two tiles from now (DRAM latency is what bounds the small-C
-            // layers: the ring can only keep a_stages * a_bytes in flight per SM)
-            const long long tp = t + 2 * (long long)gridDim.x;
+            // warm L2 with the halo tile this producer will need two of its tiles from now (DRAM latency is what bounds
+            // the small-C layers: the ring can only keep a_stages * a_bytes in flight per SM)
+            const long long tp = t + pf_dist;
             if (tp < total_tiles && elect_one()) {
                 const TileCoord pc = decode_tile(tp, a);
                 const int ptx_ = pc.tx, pty = pc.ty, pb = pc.b;
@@ -191,16 +209,23 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
             for (int kc = 0; kc < a.kchunks; ++kc) {
 #pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
+                for (int kx = 0; kx < KS; kx += KXS) {
                     const uint32_t slot = ring_base + as;
                     mbar_wait(aempty0 + 8 * slot, aph ^ 1u);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_bytes);
-                        tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0 + kx, y0, b);
+                        if (a.debug & 4) {
+                            mbar_arrive(afull0 + 8 * slot);
+                        } else {
+                            mbar_arrive_expect_tx(afull0 + 8 * slot, stage_bytes);
+#pragma unroll
+                            for (int i = 0; i < KXS; ++i)
+                                tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * stage_bytes + (uint32_t)i * a.a_bytes,
+                                            kc * a.cin_blk, x0 + kx + i, y0, b);
+                        }
                     }
                     __syncwarp();
                     if (++as == ring_n) { as = 0; aph ^= 1u; }
-                    if (!RES) {
+                    if (!RES) {                                                            // (KXS == 1 here)
                         int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*KS + kx
 #pragma unroll
                         for (int ky = 0; ky < KS; ++ky, row += row_step) {
@@ -216,7 +241,6 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
             }
-            if (ring) { as_[1] = as; aph_[1] = aph; } else { as_[0] = as; aph_[0] = aph; }
         }
     } else if (warp == 1 || warp == 3) {
         // ===================== MMA issuers (whole warp loops, one elected lane issues) =====================
@@ -232,56 +256,67 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t lo_lbo = 1u << 16;                          // LBO field (ignored for swizzled K-major), kept = 1
         constexpr uint32_t ky_step = (TC_TW * row_bytes) >> 4;         // one tile row of pixels, in 16-byte units
         const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_bytes >> 4;
+        const uint32_t st16 = (uint32_t)KXS * a16;                     // one ring stage, in 16-byte units
         const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
         const uint32_t tap16 = (uint32_t)a.kchunks * b16;              // resident weights: +1 tap
         if (RES) mbar_wait(bres, 0);
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, tile_it = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0;
         const uint32_t ring_n = a.dual ? (uint32_t)a.a_stages / 2u : (uint32_t)a.a_stages;
-        const uint32_t ring_lo0 = a_lo0 + (a.dual ? me * ring_n * a16 : 0u);
+        const uint32_t ring_lo0 = a_lo0 + (a.dual ? me * ring_n * st16 : 0u);
         const uint32_t ring_bar = a.dual ? me * ring_n : 0u;
         a_lo = ring_lo0;
+        // The accumulators form a ring of a.nacc TMEM slots (tile i -> slot i % nacc): round-1 knob experiments showed the
+        // hand-shake chain issuer -> tcgen05.commit -> epilogue -> tempty -> issuer costs ~1600 cycles per tile even with
+        // all work disabled, so with one slot per issuer every small-tile layer ran at the chain's latency.
+        uint32_t acc_c = 0, acc_p = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const uint32_t acc = acc_c, acc_ph = acc_p;
+            if (++acc_c == (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
             if (a.dual ? ((tile_it & 1u) != me) : (me != 0u)) continue;   // not this issuer's tile
-            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
             tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256u;
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_tile;
             uint32_t bkc = b_lo0;                                      // resident weights: chunk kc of tap 0
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
 #pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
+                for (int kxg = 0; kxg < KS; kxg += KXS) {
                     mbar_wait(afull0 + 8 * (ring_bar + as), aph);
                     tcgen05_fence_after();
 #pragma unroll
-                    for (int ky = 0; ky < KS; ++ky) {
-                        uint32_t bl;
-                        if (RES) {
-                            bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
-                        } else {
-                            mbar_wait(bfull0 + 8 * bs, bph);
-                            tcgen05_fence_after();
-                            bl = b_lo;
-                        }
-                        const uint32_t al = a_lo + (uint32_t)ky * ky_step;
-                        if (elect_one()) {
+                    for (int ki = 0; ki < KXS; ++ki) {
+                        const int kx = kxg + ki;
 #pragma unroll
-                            for (int kk = 0; kk < KKN; ++kk) {
-                                // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                                const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
-                                umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
+                        for (int ky = 0; ky < KS; ++ky) {
+                            uint32_t bl;
+                            if (RES) {
+                                bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
+                            } else {
+                                mbar_wait(bfull0 + 8 * bs, bph);
+                                tcgen05_fence_after();
+                                bl = b_lo;
                             }
-                            if (!RES) umma_commit(bempty0 + 8 * bs);
-                        }
-                        __syncwarp();
-                        if (!RES) {
-                            b_lo += b16;
-                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
+                            const uint32_t al = a_lo + (uint32_t)ki * a16 + (uint32_t)ky * ky_step;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int kk = 0; kk < KKN; ++kk) {
+                                    if (a.debug & 2) continue;
+                                    // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                                    const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                                    umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
+                                }
+                                if (!RES) umma_commit(bempty0 + 8 * bs);
+                            }
+                            __syncwarp();
+                            if (!RES) {
+                                b_lo += b16;
+                                if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
+                            }
                         }
                     }
                     if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
                     __syncwarp();
-                    a_lo += a16;
+                    a_lo += st16;
                     if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
                 }
             }
@@ -299,15 +334,16 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int half = a.n_tile >> 1;
         const int nchunks = half >> 4;
         const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
-        uint32_t tile_it = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+        uint32_t acc_c = 0, acc_p = 0, lean_it = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const TileCoord tc_ = decode_tile(t, a);
             const int nt = tc_.nt, tx = tc_.tx, ty = tc_.ty, b = tc_.b;
             const int x = tx * TC_TW + px, y = ty * TC_TH + py;
             const bool inside = (x < a.W) && (y < a.H);
             const long long pixo = (((long long)b * a.H + y) * a.W + x) * a.Cout + nt * half;
-            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
-            const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            const uint32_t acc = acc_c, acc_ph = acc_p;
+            if (++acc_c == (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
+            const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
 
             if (half == 8) {
                 // final layer (unet.py:285: BasicConv(32 -> 3), Cout padded to 8): one 8-column chunk, NCHW fp32 output
@@ -335,71 +371,89 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 continue;
             }
             if (NTHR == 640) {
-                // lean 16-warp path: warp = (TMEM lane quadrant q, column group sub of 8 channels), chunks sub, sub+4, ...
-                const int nch8 = half >> 3;
-                uint4 res8 = make_uint4(0, 0, 0, 0), mul8 = make_uint4(0, 0, 0, 0);
-                if (inside && sub < nch8) {
-                    if (a.residual) res8 = __ldg(reinterpret_cast<const uint4 *>(a.residual + pixo + sub * 8));
-                    if (a.out2) mul8 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + pixo + sub * 8));
+                // lean 16-warp path.  Work item = (TMEM lane quadrant q, 16-column chunk): 4 * nch16 items per tile, dealt
+                // to the 16 warps as warp -> (q, chunk k % nch16) of every G-th tile, G = 4 / nch16 (Cout 32: each warp
+                // serves alternate tiles; Cout 64: every tile).  A lane then owns 32 contiguous output bytes of its
+                // pixel: full 32-byte sectors for the residual read and the store (8-column items touched half sectors
+                // from two different warps at different times) and half as many per-tile hand-shakes per output.
+                // EPI fixes the layer kind at compile time (1: ELU, no residual - ResBlock main.0; 2: no activation +
+                // residual - ResBlock main.1; 0: runtime flags).
+                const bool elu = EPI == 1 ? true : (EPI == 2 ? false : a.elu != 0);
+                const bool has_res = EPI == 2 ? true : (EPI == 1 ? false : a.residual != nullptr);
+                const bool has_out2 = EPI != 0 ? false : a.out2 != nullptr;
+                const int nch16 = half >> 4;                       // 1, 2 or 4 (host: lean only for Cout 16 / 32 / 64)
+                const int kq = sub;                                // (warp - 4) >> 2
+                const int chunk = kq & (nch16 - 1);
+                if (((lean_it++) & (uint32_t)((4 >> (nch16 >> 1)) - 1)) != (uint32_t)(kq >> (nch16 >> 1))) continue;   // not my tile
+                if (a.debug & 1) {
+                    mbar_wait(tfull0 + 8 * acc, acc_ph);
+                    tcgen05_fence_after();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    continue;
+                }
+                const bool mem_ok = !(a.debug & 8);
+                const int co = nt * half + chunk * 16;
+                const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;                  // < 2^31 (checked by the host)
+                uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, ml0 = rs0, ml1 = rs0;
+                if (inside && mem_ok) {
+                    if (has_res) {
+                        rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                    }
+                    if (has_out2) {
+                        ml0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        ml1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
+                    }
                 }
                 mbar_wait(tfull0 + 8 * acc, acc_ph);
                 tcgen05_fence_after();
-                for (int c = sub; c < nch8; c += 4) {
-                    uint32_t f8[8], m8[8];
-                    tmem_ld8(trow + (uint32_t)(c * 8), f8);
-                    tmem_ld8(trow + (uint32_t)(half + c * 8), m8);
-                    tmem_ld_wait();
-                    const int co = nt * half + c * 8;
-                    float yv[8];
-                    if (a.elu) {            // warp-uniform: the no-activation layers skip the ex2 path entirely
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 pp = par4[co + j];
-                            yv[j] = gate_fast<true>(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, pp.z, pp.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 pp = par4[co + j];
-                            yv[j] = gate_fast<false>(__uint_as_float(f8[j]) + pp.x, __uint_as_float(m8[j]) + pp.y, pp.z, pp.w);
-                        }
-                    }
-                    if (inside) {
-                        const long long o = pixo + c * 8;
-                        if (a.residual) {
-                            const uint32_t rr[4] = {res8.x, res8.y, res8.z, res8.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = unpack_bf16x2(rr[j]);
-                                yv[2 * j] += f.x;
-                                yv[2 * j + 1] += f.y;
-                            }
-                        }
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(yv[2 * j], yv[2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(a.out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        if (a.out2) {
-                            const uint32_t mm[4] = {mul8.x, mul8.y, mul8.z, mul8.w};
-                            uint32_t p2[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
-                                const float2 mv = unpack_bf16x2(mm[j]);
-                                p2[j] = pack_bf16x2(ys.x * mv.x, ys.y * mv.y);
-                            }
-                            *reinterpret_cast<uint4 *>(a.out2 + o) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                        }
-                        const int cn = c + 4;   // next chunk of this warp (Cout = 64): fetch its residual now
-                        if (cn < nch8) {
-                            if (a.residual) res8 = __ldg(reinterpret_cast<const uint4 *>(a.residual + pixo + cn * 8));
-                            if (a.out2) mul8 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + pixo + cn * 8));
-                        }
-                    }
-                }
+                uint32_t f16[16], m16[16];
+                tmem_ld16(trow + (uint32_t)(chunk * 16), f16);
+                tmem_ld16(trow + (uint32_t)(half + chunk * 16), m16);
+                tmem_ld_wait();
+                // the accumulator is in registers: hand the TMEM slot back before the math
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                float yv[16];
+                if (elu) {              // warp-uniform: the no-activation layers skip the ex2 path entirely
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<true>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
+                }
+                if (inside && (mem_ok || yv[0] == 123.456f)) {
+                    if (has_res) {
+                        const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            yv[2 * j] += __uint_as_float(rr[j] << 16);
+                            yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = cvt_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                    uint4 *op = reinterpret_cast<uint4 *>(a.out + o);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (has_out2) {
+                        const uint32_t mm[8] = {ml0.x, ml0.y, ml0.z, ml0.w, ml1.x, ml1.y, ml1.z, ml1.w};
+                        uint32_t p2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
+                            const float2 mv = unpack_bf16x2(mm[j]);
+                            p2[j] = cvt_bf16x2(ys.x * mv.x, ys.y * mv.y);
+                        }
+                        uint4 *o2 = reinterpret_cast<uint4 *>(a.out2 + o);
+                        o2[0] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        o2[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
+                    }
+                }
                 continue;
             }
             // two statically named register buffers (A/B): runtime-indexed arrays would be demoted to local memory
@@ -647,8 +701,13 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     const uint32_t total_b = (uint32_t)(d.k * d.k * g.kchunks) * a.b_bytes;
     a.b_resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b >= 2 * a.a_bytes) ? 1 : 0;
     uint32_t b_region_bytes;
+    a.kxs = 1;
     if (a.b_resident) {
         int st = (int)((TC_SMEM_BUDGET - total_b) / a.a_bytes);
+        if (d.k == 3 && st / 3 >= 4) {        // room for >= 4 whole-tile stages: one wait / expect_tx / commit per tile
+            a.kxs = 3;
+            st /= 3;
+        }
         a.a_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         a.b_stages = 0;
         b_region_bytes = total_b;
@@ -660,9 +719,10 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     }
     a.inv_tx = 1.0f / (float)a.tiles_x;
     a.inv_ty = 1.0f / (float)a.tiles_y;
-    a.dual = (a.b_resident && a.a_stages >= 6) ? 1 : 0;
+    a.nacc = TC_TMEM_COLS / g.n_tile > TC_MAX_ACC ? TC_MAX_ACC : TC_TMEM_COLS / g.n_tile;
+    a.dual = (a.b_resident && a.a_stages >= (a.kxs == 3 ? 4 : 6)) ? 1 : 0;
     if (a.dual) a.a_stages &= ~1;            // two equal half rings
-    a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
+    a.b_region_off = (uint32_t)a.a_stages * (uint32_t)a.kxs * a.a_bytes;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
@@ -675,39 +735,54 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     return READ_OK;
 }
 
+int g_tc_debug = 0;
+
 int tc_plan_launch(const TcPlan *p, cudaStream_t st)
 {
-    const TcArgs &a = p->args;
+    TcArgs a = p->args;
+    a.debug = g_tc_debug;
     const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
-#define RB_TC_LAUNCH(KS_, KKN_, RES_)                                                                                   \
+#define RB_TC_LAUNCH_I(KS_, KKN_, RES_, NT_, EPI_, KXS_)                                                               \
     do {                                                                                                                \
-        if (lean) {                                                                                                     \
-            RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, 640>,                                     \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));             \
-            gated_conv_tc_kernel<KS_, KKN_, RES_, 640><<<(unsigned)grid, 640, p->smem_bytes, st>>>(p->tmA, p->tmB, a);   \
-        } else {                                                                                                        \
-            RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, 384>,                                     \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));             \
-            gated_conv_tc_kernel<KS_, KKN_, RES_, 384><<<(unsigned)grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, a);   \
-        }                                                                                                               \
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, KXS_>,                            \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));                 \
+        gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, KXS_><<<(unsigned)grid, NT_, p->smem_bytes, st>>>(p->tmA, p->tmB, a); \
     } while (0)
-    const bool lean = a.cout_pad >= 16 && (a.n_tile >> 1) <= 64;       // Cout 16..64: 16-warp epilogue
+#define RB_TC_LAUNCH(KS_, KKN_, RES_, KXS_)                                                                             \
+    do {                                                                                                                \
+        if (lean) RB_TC_LAUNCH_I(KS_, KKN_, RES_, 640, 0, KXS_);                                                        \
+        else RB_TC_LAUNCH_I(KS_, KKN_, RES_, 384, 0, KXS_);                                                             \
+    } while (0)
+    // lean 16-warp epilogue: Cout 16..64 and 32-bit output offsets
+    const int half_n = a.n_tile >> 1;
+    const bool lean = (half_n == 16 || half_n == 32 || half_n == 64) && a.Cout == a.cout_pad &&
+                      (long long)a.B * a.H * a.W * a.Cout < (1ll << 31);
     const int kkn = a.cin_blk / 16;
-    if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true);
-    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false);
-    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true);
-    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false);
-    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true);
-    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false);
-    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true);
-    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false);
+    const bool ts = a.kxs == 3;             // tile-granular A stages (implies ksize 3 and resident weights)
+    // the two ResBlock layer kinds of the C=32 / C=64 stages get compile-time epilogues
+    const int epi = (lean && a.ksize == 3 && a.b_resident && !a.out2) ? ((a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0)) : 0;
+    if (epi == 1 && kkn == 2 && ts) RB_TC_LAUNCH_I(3, 2, true, 640, 1, 3);
+    else if (epi == 2 && kkn == 2 && ts) RB_TC_LAUNCH_I(3, 2, true, 640, 2, 3);
+    else if (epi == 1 && kkn == 4 && !ts) RB_TC_LAUNCH_I(3, 4, true, 640, 1, 1);
+    else if (epi == 2 && kkn == 4 && !ts) RB_TC_LAUNCH_I(3, 4, true, 640, 2, 1);
+    else if (a.ksize == 3 && kkn == 4 && a.b_resident && ts) RB_TC_LAUNCH(3, 4, true, 3);
+    else if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true, 1);
+    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false, 1);
+    else if (a.ksize == 3 && kkn == 2 && a.b_resident && ts) RB_TC_LAUNCH(3, 2, true, 3);
+    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true, 1);
+    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false, 1);
+    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true, 1);
+    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false, 1);
+    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true, 1);
+    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false, 1);
     else {
         set_error("tcgen05 conv: no kernel instance for k=%d cin_blk=%d", a.ksize, a.cin_blk);
         return READ_ERR_UNSUPPORTED;
     }
+#undef RB_TC_LAUNCH_I
 #undef RB_TC_LAUNCH
     RB_LAUNCH_CHECK();
     return READ_OK;

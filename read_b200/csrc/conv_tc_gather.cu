@@ -12,9 +12,11 @@
 // 64-element blocks, N = conv_f | conv_m channels (<= 256 per tile).  Weights arrive by TMA; accumulators live in
 // TMEM (double buffered); the epilogue is the same fused bias/ELU/sigmoid/BN/residual tail as conv_tc.cu.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent): warp0 = weight TMA + TMEM alloc, warp1 = MMA issuer,
-// warps2-5 = A gather producers (thread -> fixed tile column and fixed 16-byte K chunk, 8 tile rows),
-// warps6-9 = epilogue.
+// Warp roles (832 threads, 1 CTA/SM, persistent): warp0 = weight TMA + TMEM alloc, warp1 = MMA issuer,
+// warps2-9 = A gather producers, one warp per ring stage (lane -> fixed 16-byte K chunk, 4 tile columns x 8 rows),
+// warps10-25 = epilogue (TMEM lane quadrant = warp%4, four warps per quadrant interleaved over 8-column chunks).
+// Stride is a template parameter, row validity replaces clamps, source offsets are 32-bit, the tile decode is
+// division-free, accumulators form a TMEM ring.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "ptx.cuh"
@@ -24,13 +26,16 @@
 
 namespace rb {
 
-constexpr int G_THREADS = 320;
+constexpr int G_THREADS = 832;
+constexpr int G_PROD_THREADS = 256;         // warps 2..9
+constexpr int G_EPI_WARP0 = 10;              // warps 10..25
+constexpr int G_EPI_WARPS = 16;
 constexpr int G_TW = 16, G_TH = 8;
 constexpr int G_MAX_STAGES = 8;
-constexpr uint32_t G_SMEM_BUDGET = 192 * 1024;
+constexpr uint32_t G_SMEM_BUDGET = 200 * 1024;
 constexpr int G_TMEM_COLS = 512;
+constexpr int G_MAX_ACC = 8;
 constexpr int G_KBLK = 64;                     // elements per K block (128-byte rows, SWIZZLE_128B)
-constexpr int G_LA = 2;                        // cp.async groups kept in flight behind the newest one
 
 struct GSrc {
     const __nv_bfloat16 *ptr;
@@ -38,12 +43,15 @@ struct GSrc {
 };
 
 // Per-source parameters the producers read from shared memory (dynamic indexing of the kernel-parameter constant bank
-// is slow).  Nearest resampling is one formula for identity / down / up: src = clamp((dst << shl) >> shr).
+// is slow).  Nearest resampling is one formula for identity / down / up: src = (dst << shl) >> shr; a coordinate that
+// is inside the (virtual) conv input is always inside the source, so no clamp is needed.
 struct __align__(16) SrcS {
     const __nv_bfloat16 *ptr;
-    long long plane;           // H*W*C elements per image
-    int C, W, H, rs;           // rs = W*C (row stride in elements)
-    int shl, shr, bil, pad_;
+    int plane;                 // H*W*C elements per image (< 2^31)
+    int C;
+    int rs;                    // W*C (row stride in elements)
+    int shl, shr, bil;
+    int W, H, pad0_, pad1_;    // bilinear path only
 };
 
 struct GArgs {
@@ -54,7 +62,12 @@ struct GArgs {
     int K, kblocks;
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
+    float inv_tx, inv_ty, inv_nt;   // reciprocals for the division-free tile decode
     int stages;
+    int grp;                   // ring slots per empty barrier (one tcgen05.commit releases a whole group)
+    int nacc;                  // TMEM accumulator ring depth (each n_tile columns wide)
+    int debug;                 // diagnostic knobs ("tcg_debug"): 1 = epilogue only hand-shakes, 2 = no MMAs, 4 = no gather copies
+    int any_bil;
     uint32_t a_bytes, b_bytes;
     int elu;
     const float *bias_f, *bias_m, *scale, *shift;
@@ -67,10 +80,14 @@ struct GArgs {
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// the mbarrier receives one (pre-counted) arrival from this thread once all its prior cp.async have completed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t g_pack2(float a, float b)
@@ -78,8 +95,51 @@ __device__ __forceinline__ uint32_t g_pack2(float a, float b)
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+// one F2FP per pair: lo -> bits [0,16) (lower address)
+__device__ __forceinline__ uint32_t g_cvt2(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ float2 g_unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u)); }
 
+// bilinear x4, align_corners=False (torch upsample_bilinear2d): src = max(0.25*(dst+0.5)-0.5, 0).  Only the fp32-parity
+// engine and the unit tests route a bilinear source through this kernel (the bf16 engine upsamples with its own kernel).
+__device__ __noinline__ void gather_bilinear_row(const SrcS &sv, const __nv_bfloat16 *sbase, int ix, int iy, bool valid,
+                                                 uint32_t dst)
+{
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (valid) {
+        float fx = 0.25f * ((float)ix + 0.5f) - 0.5f;
+        fx = fx < 0.f ? 0.f : fx;
+        const int x0 = (int)fx;
+        const int xp = (x0 < sv.W - 1) ? 1 : 0;
+        const float lx = fx - (float)x0, hx = 1.f - lx;
+        float fy = 0.25f * ((float)iy + 0.5f) - 0.5f;
+        fy = fy < 0.f ? 0.f : fy;
+        const int y0 = (int)fy;
+        const int yp = (y0 < sv.H - 1) ? 1 : 0;
+        const float ly = fy - (float)y0, hy = 1.f - ly;
+        const __nv_bfloat16 *p = sbase + ((long long)y0 * sv.W + x0) * sv.C;
+        const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)xp * sv.C));
+        const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)yp * sv.W * sv.C));
+        const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(p + ((long long)yp * sv.W + xp) * sv.C));
+        const uint32_t *a00 = &v00.x, *a01 = &v01.x, *a10 = &v10.x, *a11 = &v11.x;
+        uint32_t r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f00 = g_unpack2(a00[q]), f01 = g_unpack2(a01[q]), f10 = g_unpack2(a10[q]), f11 = g_unpack2(a11[q]);
+            r[q] = g_pack2(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
+                           hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
+        }
+        o = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+}
+
+template <int STRIDE>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GArgs a)
 {
@@ -93,26 +153,27 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     const uint32_t full0 = s_u32(bars);
     const uint32_t empty0 = full0 + 8 * G_MAX_STAGES;
     const uint32_t tfull0 = empty0 + 8 * G_MAX_STAGES;
-    const uint32_t tempty0 = tfull0 + 16;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * G_MAX_STAGES + 4);
-    float *s_par = reinterpret_cast<float *>(bars + 2 * G_MAX_STAGES + 6);   // 4 x Cout_pad floats
+    const uint32_t tempty0 = tfull0 + 8 * G_MAX_ACC;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * G_MAX_STAGES + 2 * G_MAX_ACC);
+    float4 *s_par4 = reinterpret_cast<float4 *>(bars + 2 * G_MAX_STAGES + 2 * G_MAX_ACC + 2);   // Cout_pad x {bias_f, bias_m, scale, shift}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CP = a.Cout_pad;
     // per-(K block, 16-byte chunk) decode table, built once per CTA so the producers' hot loop has no division:
     // {source index (-1 = zero padding of K), ky, kx, channel offset inside the source}
-    int4 *s_tab = reinterpret_cast<int4 *>(s_par + 4 * CP);
+    int4 *s_tab = reinterpret_cast<int4 *>(s_par4 + CP);
     SrcS *s_src = reinterpret_cast<SrcS *>(s_tab + a.kblocks * 8);
     if (threadIdx.x < READ_MAX_SRC) {
         const GSrc &g = a.src[threadIdx.x < a.n_src ? threadIdx.x : 0];
         SrcS v;
         v.ptr = g.ptr;
-        v.plane = (long long)g.H * g.W * g.C;
-        v.C = g.C; v.W = g.W; v.H = g.H; v.rs = g.W * g.C;
+        v.plane = g.H * g.W * g.C;
+        v.C = g.C;
+        v.rs = g.W * g.C;
         v.shl = g.mode == READ_SRC_NEAREST_DOWN ? g.shift : 0;
         v.shr = g.mode == READ_SRC_NEAREST_UP ? g.shift : 0;
         v.bil = g.mode == READ_SRC_BILINEAR_UP4 ? 1 : 0;
-        v.pad_ = 0;
+        v.W = g.W; v.H = g.H; v.pad0_ = 0; v.pad1_ = 0;
         s_src[threadIdx.x] = v;
     }
     for (int i = threadIdx.x; i < a.kblocks * 8; i += G_THREADS) {
@@ -128,22 +189,18 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         }
         s_tab[i] = e;
     }
-    for (int i = threadIdx.x; i < CP; i += G_THREADS) {
-        const bool v = i < a.Cout;
-        s_par[i] = v ? a.bias_f[i] : 0.f;
-        s_par[CP + i] = v ? a.bias_m[i] : 0.f;
-        s_par[2 * CP + i] = v ? a.scale[i] : 0.f;
-        s_par[3 * CP + i] = v ? a.shift[i] : 0.f;
-    }
+    for (int i = threadIdx.x; i < CP; i += G_THREADS)
+        s_par4[i] = i < a.Cout ? make_float4(a.bias_f[i], 0.5f * a.bias_m[i], 0.5f * a.scale[i], a.shift[i])   // gate_folded
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 1 && lane == 0) {
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < a.stages; ++s) {
-            mbar_init(full0 + 8 * s, 128 + 1);   // 128 gather threads + the weight-TMA thread
+            mbar_init(full0 + 8 * s, 32 + 1);   // the 32 lanes of the stage's gather warp + the weight-TMA thread
             mbar_init(empty0 + 8 * s, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < G_MAX_ACC; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4);
+            mbar_init(tempty0 + 8 * i, G_EPI_WARPS);         // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -160,16 +217,17 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     if (warp == 0) {
         if (lane == 0) {
             // ===================== weight TMA producer =====================
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, gi = 0, gb = empty0;   // slot, ring phase, index inside the group, group's empty barrier
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = (int)(t % a.n_tiles);
+                const int nt = (int)t - fdiv_small((int)t, a.inv_nt) * a.n_tiles;
                 int row = nt * a.n_tile;
                 for (int kb = 0; kb < a.kblocks; ++kb, row += n_total) {
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    if (gi == 0) mbar_wait(gb, ph ^ 1u);
+                    if (++gi == (uint32_t)a.grp) { gi = 0; gb += 8; }
                     const uint32_t fb = full0 + 8 * s;
                     mbar_arrive_expect_tx(fb, a.b_bytes);
                     tma_load_2d(&tmB, fb, smem_base + s * stage_bytes + a.a_bytes, 0, row);
-                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; gb = empty0; }
                 }
             }
         }
@@ -180,187 +238,201 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, 1024u, 2u) >> 32);
             const uint32_t st16 = stage_bytes >> 4, ab16 = a.a_bytes >> 4;
             const uint32_t lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
-            uint32_t s = 0, ph = 0, tile_it = 0, lo = lo0;
-            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-                const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+            uint32_t s = 0, ph = 0, lo = lo0, gi = 0, gb = empty0;
+            uint32_t acc = 0, acc_ph = 0;              // accumulator ring (see conv_tc.cu): tile i -> slot i % nacc
+            for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 256u;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_tile;
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(full0 + 8 * s, ph);
+                    fence_proxy_async();          // gathered A rows were written through the generic proxy
                     tcgen05_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < G_KBLK / 16; ++kk)
+                    for (int kk = 0; kk < G_KBLK / 16; ++kk) {
+                        if (a.debug & 2) continue;
                         umma_bf16_lohi(d_tmem, lo + 2u * kk, lo + ab16 + 2u * kk, desc_hi, idesc,
                                        kk != 0 ? 1u : (kb != 0 ? 1u : 0u));
-                    umma_commit(empty0 + 8 * s);
+                    }
+                    // ONE commit per group of slots (knob experiments: ~400 cycles per tcgen05.commit on the issuing thread's
+                    // critical path against 128 tensor cycles for a stage of an N=64 layer)
+                    if (++gi == (uint32_t)a.grp) { umma_commit(gb); gi = 0; gb += 8; }
                     lo += st16;
-                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; lo = lo0; }
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; lo = lo0; gb = empty0; }
                 }
                 umma_commit(tfull0 + 8 * acc);
+                if (++acc == (uint32_t)a.nacc) { acc = 0; acc_ph ^= 1u; }
             }
         }
-    } else if (warp < 6) {
-        // ===================== A gather producers (128 threads) =====================
-        const int t = threadIdx.x - 64;
-        const int j = t & 7;                // 16-byte chunk inside the 128-byte K row
-        const int px = t >> 3;              // tile column handled by this thread (rows r = px + 16*i, i = tile row)
-        const uint32_t dst_off = (uint32_t)px * 128u + (uint32_t)((j ^ (px & 7)) << 4);
-        uint32_t s = 0, ph = 0;           // ring slot being filled and its phase
-        uint32_t pub = 0;                 // ring slot to publish next (lags G_LA steps behind)
-        uint32_t it = 0;
+    } else if (warp < G_EPI_WARP0) {
+        // ===================== A gather producers: 8 warps, ONE WARP PER RING STAGE =====================
+        // Warp w owns ring slot w (stages <= 8 warps; a slot must have ONE producer that sees every one of its phases, or
+        // the parity wait on its empty barrier could alias two phases) and fills it on its own: lane -> (16-byte K chunk j = lane & 7, tile
+        // column px = 4*g + (lane >> 3), g = 0..3), 8 tile rows each, 32 copies per lane and stage.  Round-1 knob
+        // experiments: with 256 threads per stage the 256 serialised mbarrier arrivals alone cost ~380 cycles per
+        // stage (3x the stage's MMA time) and every warp paid the wait / decode / table latencies of every stage; here
+        // a stage costs 32 arrivals and its per-stage set-up is paid once per lane, while 8 stages are gathered
+        // concurrently by the 8 warps.
+        const uint32_t w = (uint32_t)(warp - 2);
+        const uint32_t my_empty = empty0 + 8 * (w / (uint32_t)a.grp);   // the group barrier of slot w
+        const int j = lane & 7;
+        const int pq = lane >> 3;
+        uint32_t s = 0, ph = 0;           // ring slot of the current iteration and its phase (tracked for EVERY iteration)
+        const int4 *tab = s_tab + j;
         for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
-            int mt = (int)(tl / a.n_tiles);
-            const int tx = mt % a.tiles_x;
-            mt /= a.tiles_x;
-            const int ty = mt % a.tiles_y;
-            const int b = mt / a.tiles_y;
-            const int ox = tx * G_TW + px, oy0 = ty * G_TH;
-            const int ixb = ox * a.stride - a.pad, iyb = oy0 * a.stride - a.pad;
-            const bool colok = ox < a.Wout;
-            const int rows_ok = a.Hout - oy0;
-            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const uint32_t dst0 = smem_base + s * stage_bytes + dst_off;
-                const int4 e = s_tab[kb * 8 + j];
-                const SrcS sv = s_src[e.x < 0 ? 0 : e.x];
-                const int ix = ixb + e.z;
-                const bool xvalid = (e.x >= 0) && colok && ((unsigned)ix < (unsigned)a.Win);
-                const int iy0 = iyb + e.y;
-                const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.plane + e.w;
-                if (!sv.bil) {
-                    int sx = (ix << sv.shl) >> sv.shr;
-                    sx = min(max(sx, 0), sv.W - 1);
-                    const __nv_bfloat16 *colp = sbase + sx * sv.C;
-                    int iy = iy0;
+            const int mt = fdiv_small((int)tl, a.inv_nt);
+            const int q_ = fdiv_small(mt, a.inv_tx);
+            const int tx = mt - q_ * a.tiles_x;
+            const int b = fdiv_small(q_, a.inv_ty);
+            const int ty = q_ - b * a.tiles_y;
+            const int oy0 = ty * G_TH;
+            const int iyb = oy0 * STRIDE - a.pad;
+            const int rows_ok = a.Hout - oy0;          // tile rows i < rows_ok produce output
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                if (s == w) {
+                    mbar_wait(my_empty, ph ^ 1u);
+                    const uint32_t dst0 = smem_base + s * stage_bytes;
+                    if (a.debug & 4) {
+                        mbar_arrive(full0 + 8 * s);
+                    } else {
+                        const int4 e = tab[kb * 8];
+                        const SrcS &sv = s_src[e.x < 0 ? 0 : e.x];
+                        const __nv_bfloat16 *sbase = sv.ptr + (long long)b * sv.plane;
+                        const int iy0 = iyb + e.y;
+                        if (!sv.bil) {
+                            const int shl = sv.shl, shr = sv.shr, rs = sv.rs, C = sv.C;
+                            // per-row source offsets (elements), -1 = row outside the image / the output
+                            int roff[G_TH];
 #pragma unroll
-                    for (int i = 0; i < G_TH; ++i, iy += a.stride) {
-                        const bool valid = xvalid && (i < rows_ok) && ((unsigned)iy < (unsigned)a.Hin);
-                        int sy = (iy << sv.shl) >> sv.shr;
-                        sy = min(max(sy, 0), sv.H - 1);
-                        const __nv_bfloat16 *p = colp + (long long)sy * sv.rs;
-                        cp_async16(dst0 + (uint32_t)i * 2048u, valid ? (const void *)p : (const void *)sv.ptr, valid ? 16u : 0u);
-                    }
-                } else {
-                    // bilinear x4, align_corners=False (torch upsample_bilinear2d): src = max(0.25*(dst+0.5)-0.5, 0)
-                    float fx = 0.25f * ((float)ix + 0.5f) - 0.5f;
-                    fx = fx < 0.f ? 0.f : fx;
-                    const int x0 = (int)fx;
-                    const int xp = (x0 < sv.W - 1) ? 1 : 0;
-                    const float lx = fx - (float)x0, hx = 1.f - lx;
-#pragma unroll 2
-                    for (int i = 0; i < G_TH; ++i) {
-                        const int iy = iy0 + i * a.stride;
-                        const bool valid = xvalid && (i < rows_ok) && (iy >= 0) && (iy < a.Hin);
-                        uint4 o = make_uint4(0, 0, 0, 0);
-                        if (valid) {
-                            float fy = 0.25f * ((float)iy + 0.5f) - 0.5f;
-                            fy = fy < 0.f ? 0.f : fy;
-                            const int y0 = (int)fy;
-                            const int yp = (y0 < sv.H - 1) ? 1 : 0;
-                            const float ly = fy - (float)y0, hy = 1.f - ly;
-                            const __nv_bfloat16 *p = sbase + ((long long)y0 * sv.W + x0) * sv.C;
-                            const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(p));
-                            const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)xp * sv.C));
-                            const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(p + (long long)yp * sv.W * sv.C));
-                            const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(p + ((long long)yp * sv.W + xp) * sv.C));
-                            const uint32_t *a00 = &v00.x, *a01 = &v01.x, *a10 = &v10.x, *a11 = &v11.x;
-                            uint32_t r[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f00 = g_unpack2(a00[q]), f01 = g_unpack2(a01[q]), f10 = g_unpack2(a10[q]), f11 = g_unpack2(a11[q]);
-                                r[q] = g_pack2(hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x),
-                                               hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y));
+                            for (int i = 0; i < G_TH; ++i) {
+                                const int iy = iy0 + i * STRIDE;
+                                const bool rv = (e.x >= 0) && (i < rows_ok) && ((unsigned)iy < (unsigned)a.Hin);
+                                roff[i] = rv ? ((iy << shl) >> shr) * rs + e.w : -1;
                             }
-                            o = make_uint4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int px = g * 4 + pq;
+                                const int ox = tx * G_TW + px;
+                                const int ix = ox * STRIDE - a.pad + e.z;
+                                const bool xv = (ox < a.Wout) && ((unsigned)ix < (unsigned)a.Win);
+                                const int xoff = ((ix << shl) >> shr) * C;
+                                const uint32_t dcol = dst0 + (uint32_t)px * 128u + (uint32_t)((j ^ (px & 7)) << 4);
+#pragma unroll
+                                for (int i = 0; i < G_TH; ++i) {
+                                    const bool valid = xv && roff[i] >= 0;
+                                    cp_async16(dcol + (uint32_t)i * 2048u, sbase + (valid ? roff[i] + xoff : 0), valid ? 16u : 0u);
+                                }
+                            }
+                            // asynchronous arrival: the barrier counts this lane in when its copies above have landed (no
+                            // wait, no writer-side proxy fence: the MMA thread fences once per stage after its wait)
+                            cp_async_arrive_noinc(full0 + 8 * s);
+                        } else {
+                            for (int g = 0; g < 4; ++g) {
+                                const int px = g * 4 + pq;
+                                const int ox = tx * G_TW + px;
+                                const int ix = ox * STRIDE - a.pad + e.z;
+                                const bool xv = (e.x >= 0) && (ox < a.Wout) && ((unsigned)ix < (unsigned)a.Win);
+                                const uint32_t dcol = dst0 + (uint32_t)px * 128u + (uint32_t)((j ^ (px & 7)) << 4);
+                                for (int i = 0; i < G_TH; ++i) {
+                                    const int iy = iy0 + i * STRIDE;
+                                    const bool valid = xv && (i < rows_ok) && (iy >= 0) && (iy < a.Hin);
+                                    gather_bilinear_row(sv, sbase + e.w, ix, iy, valid, dcol + (uint32_t)i * 2048u);
+                                }
+                            }
+                            fence_proxy_async();          // plain st.shared data: writer-side fence + ordinary arrive
+                            mbar_arrive(full0 + 8 * s);
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)i * 2048u), "r"(o.x), "r"(o.y),
-                                     "r"(o.z), "r"(o.w)
-                                     : "memory");
                     }
-                }
-                cp_async_commit();
-                if (it >= (uint32_t)G_LA) {
-                    cp_async_wait<G_LA>();
-                    fence_proxy_async();
-                    mbar_arrive(full0 + 8 * pub);
-                    if (++pub == (uint32_t)a.stages) pub = 0;
                 }
                 if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
             }
         }
-        // drain: publish the last min(it, G_LA) stages
-        cp_async_wait<0>();
-        fence_proxy_async();
-        const uint32_t left = it < (uint32_t)G_LA ? it : (uint32_t)G_LA;
-        for (uint32_t k = 0; k < left; ++k) {
-            mbar_arrive(full0 + 8 * pub);
-            if (++pub == (uint32_t)a.stages) pub = 0;
-        }
     } else {
-        // ===================== epilogue (warps 6-9) =====================
-        const int q = warp & 3;
+        // ===================== epilogue (warps 10-25) =====================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int sub = (warp - G_EPI_WARP0) >> 2;    // 0..3: 8-column chunks sub, sub + 4, ...
         const int r = q * 32 + lane;
         const int py = r / G_TW, pxl = r % G_TW;
         const int half = a.n_tile >> 1;
-        uint32_t tile_it = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-            const int nt = (int)(t % a.n_tiles);
-            int mt = (int)(t / a.n_tiles);
-            const int tx = mt % a.tiles_x;
-            mt /= a.tiles_x;
-            const int ty = mt % a.tiles_y;
-            const int b = mt / a.tiles_y;
+        uint32_t acc_c = 0, acc_p = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int mt = fdiv_small((int)t, a.inv_nt);
+            const int nt = (int)t - mt * a.n_tiles;
+            const int q_ = fdiv_small(mt, a.inv_tx);
+            const int tx = mt - q_ * a.tiles_x;
+            const int b = fdiv_small(q_, a.inv_ty);
+            const int ty = q_ - b * a.tiles_y;
             const int x = tx * G_TW + pxl, y = ty * G_TH + py;
             const bool inside = (x < a.Wout) && (y < a.Hout);
-            const long long pix = ((long long)b * a.Hout + y) * a.Wout + x;
-            const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+            const int pix = (b * a.Hout + y) * a.Wout + x;                  // output elements < 2^31 (checked by the host)
+            const uint32_t acc = acc_c, acc_ph = acc_p;
+            if (++acc_c == (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
+            const bool nhwc = a.out_mode != READ_OUT_NCHW_F32;
+            const bool has_res = a.residual != nullptr, has_out2 = a.out2 != nullptr;
+            const int c_first = sub * 8;
+            // first chunk's residual / FAM multiplier: issued before the wait for the MMAs
+            uint4 r0 = make_uint4(0, 0, 0, 0), m0 = make_uint4(0, 0, 0, 0);
+            if (inside && nhwc && c_first < half && nt * half + c_first < a.Cout) {
+                const int o = pix * a.Cout + nt * half + c_first;
+                if (has_res) r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                if (has_out2) m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+            }
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tcgen05_fence_after();
-            const uint32_t trow = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < half; c0 += 8) {
+            if (a.debug & 1) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                continue;
+            }
+            const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
+            for (int c0 = c_first; c0 < half; c0 += 8 * (G_EPI_WARPS / 4)) {
+                const int co = nt * half + c0;
+                if (co >= a.Cout) break;             // padded channels (warp-uniform)
                 uint32_t rf[8], rm[8];
                 tmem_ld8(trow + (uint32_t)c0, rf);
                 tmem_ld8(trow + (uint32_t)(half + c0), rm);
+                const int o = pix * a.Cout + co;
+                if (c0 != c_first && inside && nhwc) {
+                    if (has_res) r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                    if (has_out2) m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                }
                 tmem_ld_wait();
-                const int co = nt * half + c0;
-                if (co >= a.Cout) continue;          // padded channels (warp-uniform)
                 float yv[8];
+                if (a.elu) {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    yv[jj] = gated_epilogue_fast(__uint_as_float(rf[jj]) + s_par[co + jj], __uint_as_float(rm[jj]) + s_par[CP + co + jj],
-                                                 a.elu, s_par[2 * CP + co + jj], s_par[3 * CP + co + jj]);
+                    for (int jj = 0; jj < 8; ++jj) yv[jj] = gate_folded<true>(__uint_as_float(rf[jj]), __uint_as_float(rm[jj]), s_par4[co + jj]);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) yv[jj] = gate_folded<false>(__uint_as_float(rf[jj]), __uint_as_float(rm[jj]), s_par4[co + jj]);
+                }
                 if (inside) {
-                    if (a.out_mode == READ_OUT_NCHW_F32) {
-                        float *o = static_cast<float *>(a.out);
+                    if (!nhwc) {
+                        float *op = static_cast<float *>(a.out);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj)
-                            if (co + jj < a.Cout) o[(((long long)b * a.Cout + co + jj) * a.Hout + y) * a.Wout + x] = yv[jj];
+                            if (co + jj < a.Cout) op[(((long long)b * a.Cout + co + jj) * a.Hout + y) * a.Wout + x] = yv[jj];
                     } else {
-                        const long long o = pix * a.Cout + co;
-                        if (a.residual) {
-                            const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        if (has_res) {
                             const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w};
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
-                                const float2 f = g_unpack2(rr[jj]);
-                                yv[2 * jj] += f.x;
-                                yv[2 * jj + 1] += f.y;
+                                yv[2 * jj] += __uint_as_float(rr[jj] << 16);
+                                yv[2 * jj + 1] += __uint_as_float(rr[jj] & 0xFFFF0000u);
                             }
                         }
                         uint32_t pk[4];
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) pk[jj] = g_pack2(yv[2 * jj], yv[2 * jj + 1]);
+                        for (int jj = 0; jj < 4; ++jj) pk[jj] = g_cvt2(yv[2 * jj], yv[2 * jj + 1]);
                         *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(a.out) + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        if (a.out2) {
-                            const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        if (has_out2) {
                             const uint32_t mm[4] = {m0.x, m0.y, m0.z, m0.w};
                             uint32_t p2[4];
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
                                 const float2 ys = g_unpack2(pk[jj]);
                                 const float2 mv = g_unpack2(mm[jj]);
-                                p2[jj] = g_pack2(ys.x * mv.x, ys.y * mv.y);
+                                p2[jj] = g_cvt2(ys.x * mv.x, ys.y * mv.y);
                             }
                             *reinterpret_cast<uint4 *>(a.out2 + o) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
                         }
@@ -506,31 +578,63 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
     a.tiles_x = (d.Wout + G_TW - 1) / G_TW;
     a.tiles_y = (d.Hout + G_TH - 1) / G_TH;
+    a.inv_tx = 1.0f / (float)a.tiles_x;
+    a.inv_ty = 1.0f / (float)a.tiles_y;
+    a.inv_nt = 1.0f / (float)a.n_tiles;
+    a.nacc = G_TMEM_COLS / g.n_tile > G_MAX_ACC ? G_MAX_ACC : G_TMEM_COLS / g.n_tile;
+    if ((long long)d.B * d.Hout * d.Wout * d.Cout >= (1ll << 31)) {
+        set_error("tcgen05 gather conv: output too large for 32-bit offsets");
+        delete p;
+        return READ_ERR_UNSUPPORTED;
+    }
+    a.debug = 0;
+    if ((long long)a.tiles_x * a.tiles_y * d.B * a.n_tiles >= (1ll << 22)) {
+        set_error("tcgen05 gather conv: too many tiles for the division-free decode");
+        delete p;
+        return READ_ERR_UNSUPPORTED;
+    }
     a.a_bytes = 128u * G_KBLK * 2u;
     a.b_bytes = (uint32_t)g.n_tile * G_KBLK * 2u;
     int stages = (int)(G_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
     if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
     a.stages = stages;
+    a.grp = 1;      // slots per empty barrier.  Measured: grouping (one tcgen05.commit per half ring) made every layer SLOWER
+                    // (AFF0 359 -> 400 us): the commit is not what bounds the issuing thread; kept as a knob.
+    a.any_bil = 0;
+    for (int i = 0; i < d.n_src; ++i) a.any_bil |= d.src[i].mode == READ_SRC_BILINEAR_UP4;
+    if (stages < 3 || (d.stride != 1 && d.stride != 2)) {
+        set_error("tcgen05 gather conv: unsupported geometry (stages %d, stride %d)", stages, d.stride);
+        delete p;
+        return READ_ERR_UNSUPPORTED;
+    }
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
     a.out = d.out; a.out_mode = d.out_mode;
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
-    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 6) + 16 * (size_t)g.cout_pad + 16 * (size_t)g.kblocks * 8 + sizeof(SrcS) * READ_MAX_SRC + 64;
+    p->smem_bytes = 1024 + (size_t)stages * (a.a_bytes + a.b_bytes) + 8 * (2 * G_MAX_STAGES + 2 * G_MAX_ACC + 2) + 16 * (size_t)g.cout_pad + 16 * (size_t)g.kblocks * 8 + sizeof(SrcS) * READ_MAX_SRC + 64;
     *out = p;
     return READ_OK;
 }
 
+int g_tcg_debug = 0;
+
 int tcg_plan_launch(const TcgPlan *p, cudaStream_t st)
 {
-    const GArgs &a = p->args;
+    GArgs a = p->args;
+    a.debug = g_tcg_debug;
     const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
-    RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
-    gated_conv_tc_gather_kernel<<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+    if (a.stride == 1) {
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+        gated_conv_tc_gather_kernel<1><<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+    } else {
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+        gated_conv_tc_gather_kernel<2><<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+    }
     RB_LAUNCH_CHECK();
     return READ_OK;
 }
