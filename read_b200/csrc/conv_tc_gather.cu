@@ -64,8 +64,8 @@ struct GArgs {
     int tiles_x, tiles_y;
     float inv_tx, inv_ty, inv_nt;   // reciprocals for the division-free tile decode
     int stages;
-    int grp;                   // ring slots per empty barrier (one tcgen05.commit releases a whole group)
     int nacc;                  // TMEM accumulator ring depth (each n_tile columns wide)
+    int lean16;                // epilogue work items = (quadrant, 16-column chunk) dealt over tiles (NHWC, Cout 16 / 32 / 64)
     int debug;                 // diagnostic knobs ("tcg_debug"): 1 = epilogue only hand-shakes, 2 = no MMAs, 4 = no gather copies
     int any_bil;
     uint32_t a_bytes, b_bytes;
@@ -200,7 +200,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         }
         for (int i = 0; i < G_MAX_ACC; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, G_EPI_WARPS);         // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * i, a.lean16 ? (uint32_t)(a.n_tile >> 3) : (uint32_t)G_EPI_WARPS);   // arrivals per tile
         }
         mbar_fence_init();
     }
@@ -217,35 +217,43 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     if (warp == 0) {
         if (lane == 0) {
             // ===================== weight TMA producer =====================
-            uint32_t s = 0, ph = 0, gi = 0, gb = empty0;   // slot, ring phase, index inside the group, group's empty barrier
+            uint32_t s = 0, ph = 0;
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = (int)t - fdiv_small((int)t, a.inv_nt) * a.n_tiles;
                 int row = nt * a.n_tile;
                 for (int kb = 0; kb < a.kblocks; ++kb, row += n_total) {
-                    if (gi == 0) mbar_wait(gb, ph ^ 1u);
-                    if (++gi == (uint32_t)a.grp) { gi = 0; gb += 8; }
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const uint32_t fb = full0 + 8 * s;
                     mbar_arrive_expect_tx(fb, a.b_bytes);
                     tma_load_2d(&tmB, fb, smem_base + s * stage_bytes + a.a_bytes, 0, row);
-                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; gb = empty0; }
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
+            // (Two issuers on alternate tiles were tried and dropped: both would walk the SAME stage ring, and an issuer
+            // skipping the other's stages can get more than one mbarrier phase ahead of a slot - the parity wait then
+            // aliases.  conv_tc.cu can do it because each of its issuers owns a half ring.)
+            // The ~90-cycle latency of try_wait is taken off the per-stage chain by probing the NEXT stage's barrier
+            // before the current stage's MMAs are issued.
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, 1024u, 2u) >> 32);
             const uint32_t st16 = stage_bytes >> 4, ab16 = a.a_bytes >> 4;
             const uint32_t lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
-            uint32_t s = 0, ph = 0, lo = lo0, gi = 0, gb = empty0;
+            uint32_t s = 0, ph = 0, lo = lo0;
             uint32_t acc = 0, acc_ph = 0;              // accumulator ring (see conv_tc.cu): tile i -> slot i % nacc
+            bool ready = false;                        // the current stage's full barrier was already seen complete
             for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_tile;
                 for (int kb = 0; kb < a.kblocks; ++kb) {
-                    mbar_wait(full0 + 8 * s, ph);
+                    if (!ready) mbar_wait(full0 + 8 * s, ph);
+                    uint32_t sn = s + 1, phn = ph;
+                    if (sn == (uint32_t)a.stages) { sn = 0; phn ^= 1u; }
+                    ready = mbar_try_wait(full0 + 8 * sn, phn);      // probe (the ring is continuous across tiles)
                     fence_proxy_async();          // gathered A rows were written through the generic proxy
                     tcgen05_fence_after();
 #pragma unroll
@@ -254,11 +262,10 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                         umma_bf16_lohi(d_tmem, lo + 2u * kk, lo + ab16 + 2u * kk, desc_hi, idesc,
                                        kk != 0 ? 1u : (kb != 0 ? 1u : 0u));
                     }
-                    // ONE commit per group of slots (knob experiments: ~400 cycles per tcgen05.commit on the issuing thread's
-                    // critical path against 128 tensor cycles for a stage of an N=64 layer)
-                    if (++gi == (uint32_t)a.grp) { umma_commit(gb); gi = 0; gb += 8; }
+                    umma_commit(empty0 + 8 * s);
                     lo += st16;
-                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; lo = lo0; gb = empty0; }
+                    s = sn; ph = phn;
+                    if (s == 0) lo = lo0;
                 }
                 umma_commit(tfull0 + 8 * acc);
                 if (++acc == (uint32_t)a.nacc) { acc = 0; acc_ph ^= 1u; }
@@ -274,7 +281,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         // a stage costs 32 arrivals and its per-stage set-up is paid once per lane, while 8 stages are gathered
         // concurrently by the 8 warps.
         const uint32_t w = (uint32_t)(warp - 2);
-        const uint32_t my_empty = empty0 + 8 * (w / (uint32_t)a.grp);   // the group barrier of slot w
+        const uint32_t my_empty = empty0 + 8 * w;
         const int j = lane & 7;
         const int pq = lane >> 3;
         uint32_t s = 0, ph = 0;           // ring slot of the current iteration and its phase (tracked for EVERY iteration)
@@ -347,14 +354,14 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < G_EPI_WARP0 + G_EPI_WARPS) {
         // ===================== epilogue (warps 10-25) =====================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int sub = (warp - G_EPI_WARP0) >> 2;    // 0..3: 8-column chunks sub, sub + 4, ...
         const int r = q * 32 + lane;
         const int py = r / G_TW, pxl = r % G_TW;
         const int half = a.n_tile >> 1;
-        uint32_t acc_c = 0, acc_p = 0;
+        uint32_t acc_c = 0, acc_p = 0, lean_it = 0;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int mt = fdiv_small((int)t, a.inv_nt);
             const int nt = (int)t - mt * a.n_tiles;
@@ -369,6 +376,83 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             if (++acc_c == (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
             const bool nhwc = a.out_mode != READ_OUT_NCHW_F32;
             const bool has_res = a.residual != nullptr, has_out2 = a.out2 != nullptr;
+            if (a.lean16) {
+                // (quadrant, 16-column chunk) items, 4 * nch16 per tile, dealt warp -> chunk (sub % nch16) of every G-th
+                // tile (G = 4 / nch16): a lane owns 32 contiguous output bytes (full sectors), see conv_tc.cu
+                const int nch16 = half >> 4;
+                const int chunk = sub & (nch16 - 1);
+                if (((lean_it++) & (uint32_t)((4 >> (nch16 >> 1)) - 1)) != (uint32_t)(sub >> (nch16 >> 1))) continue;
+                const int co = chunk * 16;
+                const int o = pix * a.Cout + co;
+                uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, ml0 = rs0, ml1 = rs0;
+                if (inside) {
+                    if (has_res) {
+                        rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                    }
+                    if (has_out2) {
+                        ml0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        ml1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
+                    }
+                }
+                mbar_wait(tfull0 + 8 * acc, acc_ph);
+                tcgen05_fence_after();
+                const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
+                if (a.debug & 1) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    continue;
+                }
+                // two 8-column halves in sequence (register budget: 72 per thread at 832 threads)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t f8[8], m8[8];
+                    tmem_ld8(trow + (uint32_t)(co + 8 * hh), f8);
+                    tmem_ld8(trow + (uint32_t)(half + co + 8 * hh), m8);
+                    tmem_ld_wait();
+                    if (hh == 1) {                    // accumulator fully read: hand the TMEM slot back before the math
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    }
+                    float yv[8];
+                    if (a.elu) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) yv[jj] = gate_folded<true>(__uint_as_float(f8[jj]), __uint_as_float(m8[jj]), s_par4[co + 8 * hh + jj]);
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) yv[jj] = gate_folded<false>(__uint_as_float(f8[jj]), __uint_as_float(m8[jj]), s_par4[co + 8 * hh + jj]);
+                    }
+                    if (inside) {
+                        const uint4 rs = hh ? rs1 : rs0, ml = hh ? ml1 : ml0;
+                        if (has_res) {
+                            const uint32_t rr[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                yv[2 * jj] += __uint_as_float(rr[jj] << 16);
+                                yv[2 * jj + 1] += __uint_as_float(rr[jj] & 0xFFFF0000u);
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) pk[jj] = g_cvt2(yv[2 * jj], yv[2 * jj + 1]);
+                        reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(a.out) + o)[hh] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (has_out2) {
+                            const uint32_t mm[4] = {ml.x, ml.y, ml.z, ml.w};
+                            uint32_t p2[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float2 ys = g_unpack2(pk[jj]);
+                                const float2 mv = g_unpack2(mm[jj]);
+                                p2[jj] = g_cvt2(ys.x * mv.x, ys.y * mv.y);
+                            }
+                            reinterpret_cast<uint4 *>(a.out2 + o)[hh] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        }
+                    }
+                }
+                continue;
+            }
             const int c_first = sub * 8;
             // first chunk's residual / FAM multiplier: issued before the wait for the MMAs
             uint4 r0 = make_uint4(0, 0, 0, 0), m0 = make_uint4(0, 0, 0, 0);
@@ -588,6 +672,8 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
         return READ_ERR_UNSUPPORTED;
     }
     a.debug = 0;
+    a.lean16 = (d.out_mode == READ_OUT_NHWC && g.n_tiles == 1 && g.cout_pad == d.Cout &&
+                (d.Cout == 16 || d.Cout == 32 || d.Cout == 64)) ? 1 : 0;
     if ((long long)a.tiles_x * a.tiles_y * d.B * a.n_tiles >= (1ll << 22)) {
         set_error("tcgen05 gather conv: too many tiles for the division-free decode");
         delete p;
@@ -598,8 +684,6 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     int stages = (int)(G_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
     if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
     a.stages = stages;
-    a.grp = 1;      // slots per empty barrier.  Measured: grouping (one tcgen05.commit per half ring) made every layer SLOWER
-                    // (AFF0 359 -> 400 us): the commit is not what bounds the issuing thread; kept as a knob.
     a.any_bil = 0;
     for (int i = 0; i < d.n_src; ++i) a.any_bil |= d.src[i].mode == READ_SRC_BILINEAR_UP4;
     if (stages < 3 || (d.stride != 1 && d.stride != 2)) {

@@ -178,6 +178,8 @@ TC_CASES = [
     ("C64 1x1", [(64, 8, 16, "id", 1)], 64, 1, True, {}),
     ("C32 -> 64 channels, FAM product output", [(32, 16, 16, "id", 1)], 64, 3, True, {"out2": True}),
     ("many tiles per CTA (persistence, phases wrap)", [(32, 200, 208, "id", 1)], 32, 3, True, {"residual": True}),
+    ("persistent C32, 2560 tiles (17 per CTA)", [(32, 512, 640, "id", 1)], 32, 3, True, {}),
+    ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
     ("final layer 32->3, NCHW f32 output", [(32, 24, 40, "id", 1)], 3, 3, False, {"final": True}),
 ]
 
@@ -204,6 +206,10 @@ GATHER_CASES = [c for c in GENERIC_CASES if not c[6].get("mul")] + [
     ("3x3 s2 128->256", [(128, 16, 16, "id", 1)], 256, 3, 2, True, {"out2": True}),
     ("4x4 s2 256->128", [(256, 16, 16, "id", 1)], 128, 4, 2, True, {}),
     ("many tiles (phases wrap), s2", [(32, 256, 320, "id", 1)], 64, 3, 2, True, {}),
+    # persistence: 17+ tiles per CTA so every ring (stages, TMEM accumulators, epilogue dealing) wraps several times
+    ("persistent 1x1 32->32 + residual, 2560 tiles", [(32, 512, 640, "id", 1)], 32, 1, 1, True, {"residual": True}),
+    ("persistent 3x3 8->32, 2 k-blocks per tile, 2560 tiles", [(8, 512, 640, "id", 1)], 32, 3, 1, True, {}),
+    ("persistent concat 32+32 -> 64 1x1, 2560 tiles", [(32, 512, 640, "id", 1), (32, 256, 320, "up", 2)], 64, 1, 1, False, {}),
 ]
 
 

@@ -41,6 +41,49 @@ def test_random_scenes_bit_exact(oracle_mod, n, W, H, L, ts):
     _check(oracle_mod, xyz, M, W, H, L)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_every_single_view_kernel_variant_is_bit_exact(oracle_mod, mode):
+    """B == 1 with nested levels can run the staged kernel (0) or the lean kernel (1: RED only, 2: early-z + RED,
+    3: shared-memory filter + RED); all must produce the oracle's packed z-buffer bit for bit."""
+    from read_b200 import _lib as L
+    lib = L.load()
+    try:
+        L.check(lib.read_set_option(b"raster_mode", mode))
+        for n, W, H, Lv, t in ((100_000, 256, 256, 5, 0), (300_000, 128, 64, 3, 4), (4097, 64, 32, 2, 9)):
+            xyz, M = scene_and_cams(n, W, H, [t], depth=40.0)      # heavy overdraw: many points per pixel
+            _check(oracle_mod, xyz, M, W, H, Lv)
+    finally:
+        L.check(lib.read_set_option(b"raster_mode", 2))
+
+
+def test_shared_reciprocal_division_edge_values(oracle_mod):
+    """The lean kernel replaces three IEEE divisions by one reciprocal + residual corrections and culls before dividing.
+    Points exactly on the frustum planes (|a| == |w|), one ulp either side of them, huge / tiny w and w == 0 must
+    give the oracle's result bit for bit (the oracle divides with the C '/' operator)."""
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, size=(4000, 3)).astype(np.float32)
+    w = np.exp(rng.uniform(-60, 60, size=4000)).astype(np.float32)
+    w[:50] = 0.0
+    w[50:100] = np.float32(1e-42)                  # denormal w -> fallback path
+    w[100:150] = np.float32(3e38)
+    pts = base.copy()
+    # x, y, z on the planes and one ulp off them
+    pts[:1000, 0] = np.where(rng.random(1000) < 0.5, 1.0, -1.0)
+    pts[1000:1500, 0] = np.nextafter(np.float32(1.0), np.float32(2.0))
+    pts[1500:2000, 1] = np.nextafter(np.float32(1.0), np.float32(0.0))
+    pts[2000:2500, 2] = -1.0
+    pts[2500:3000, 2] = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    # matrix = diag(1,1,1,0) with w taken from a 4th "coordinate": emulate per-point w by scaling the point and using
+    # M[3] = (0,0,0,1) * s ... simpler: fold w into the points (clip = (x*w, y*w, z*w, w)) with M's last row (0,0,1,0)
+    # reading w from z: z' = w, and x' = x*w, y' = y*w, with depth row = (0,0,c,0) so cz = c exactly.
+    xyz = np.stack([pts[:, 0] * w, pts[:, 1] * w, w], axis=1).astype(np.float32)
+    for c in (np.float32(0.25), np.float32(-0.5), np.float32(1.0)):
+        M = np.zeros((1, 4, 4), np.float32)
+        M[0, 0, 0] = 1; M[0, 1, 1] = 1; M[0, 2, 2] = c; M[0, 3, 2] = 1
+        _check(oracle_mod, xyz, M, 64, 48, 1)
+        _check(oracle_mod, xyz, M, 1920, 1088, 1)
+
+
 def test_c2_one_million_points_512(oracle_mod):
     xyz, M = scene_and_cams(1_000_000, 512, 512, [3], depth=250.0, seed=synth.SEED)
     _check(oracle_mod, xyz, M, 512, 512, 4)
