@@ -38,6 +38,15 @@ WORKLOAD = ("synthetic 10M-point street scene, 1920x1080 (rendered 1920x1088: pa
             "L=4 pyramid, descriptor dim 8, full MIMO-UNet refine")
 
 
+def measured_traffic():
+    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -372,16 +381,22 @@ def run_ours(args):
     hbm = pk["hbm_gbs"]
     tens_peak = pk["bf16_tflops_sustained"]
     roof_tc = None
+    traf = measured_traffic()
     if tc_ms > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
         roof_tc = {"kernel": "gated_conv_tc_kernel (tcgen05 implicit-GEMM gated conv)", "bound": "tensor",
                    "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
-                   "peak_src": pk["src"] + " (sustained bf16)", "traffic": None, "ms_per_frame": tc_ms,
+                   "peak_src": pk["src"] + " (sustained bf16)",
+                   "traffic": (traf or {}).get("gated_conv_tc_kernel_avg_bytes_per_launch"),
+                   "traffic_src": "profiles/r01_traffic.json (ncu dram bytes, average over the 76 launches)" if traf else None,
+                   "ms_per_frame": tc_ms,
                    "layers": sum(1 for l_ in eng.layers if l_.impl == L.CONV_TCGEN05)}
     ach_r = rg_bytes / (rg_ms * 1e-3) / 1e9
-    roof_raster = {"kernel": "raster_project_kernel + pyramid_resolve_gather_kernel", "bound": "hbm",
+    roof_raster = {"kernel": "raster_lean_kernel + pyramid_resolve_gather_kernel", "bound": "hbm",
                    "achieved": ach_r, "peak": hbm, "unit": "GB/s", "frac": ach_r / hbm, "peak_src": pk["src"],
-                   "traffic": None, "algorithmic_bytes": rg_bytes, "ms_per_frame": rg_ms,
+                   "traffic": ((traf["raster_lean_kernel_bytes_per_launch"] + traf["pyramid_resolve_gather_bytes_per_launch"])
+                               if traf else None),
+                   "algorithmic_bytes": rg_bytes, "ms_per_frame": rg_ms,
                    "project_ms": project_ms, "resolve_gather_ms": resolve_ms}
     gen_ach = gen_flops / (gen_ms * 1e-3) / 1e12 if gen_ms > 0 else None
     tcg_ach = tcg_flops / (tcg_ms * 1e-3) / 1e12 if tcg_ms > 0 else None
