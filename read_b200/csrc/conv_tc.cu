@@ -3,14 +3,19 @@
 // One kernel computes  y = BN( A(conv_f(x)+b_f) * sigmoid(conv_m(x)+b_m) ) [+ residual]  (BasicConv,
 // READ/models/unet.py:22-53) for stride-1 k x k convolutions over NHWC bf16 activations:
 //
-//   GEMM view   D[M = 128 output pixels (8 rows x 16 cols of one image), N = f|m channels] +=
+//   GEMM view   D[M = 128 output pixels (16 rows x 8 cols of one image), N = f|m channels] +=
 //               A[M, K = one filter tap x CIN_BLK input channels] * B[N, K]
-//   A operand   ONE TMA 4-D tile load {c, x, y, b} per filter COLUMN kx: a (8+k-1)-row x 16-col halo tile at the
-//               kx-shifted position; the k filter ROWS reuse it through UMMA descriptors whose start address is
-//               advanced by ky*16 pixel rows (a whole number of swizzle atoms), so the input is fetched from L2
-//               k times per tile instead of k*k times.  Pixels outside the image are ZERO-FILLED by the TMA unit
-//               == the conv's zero padding (unet.py:29,36).  Rows are CIN_BLK bf16 (64 or 128 bytes) with the
-//               matching 64B/128B swizzle: the canonical K-major UMMA layout, no im2col is ever materialised.
+//   A operand   ONE TMA 4-D tile load {c, x, y, b} per tile and K chunk: the (16+k-1)-row x (8+k-1)-column halo tile.
+//               Every filter tap (ky, kx) reads it through a UMMA descriptor whose start address is advanced by
+//               (ky * halo_w + kx) pixel rows and whose 8-row-group stride (SBO) is halo_w pixel rows: tcgen05.mma
+//               addresses the rows of a swizzled K-major operand linearly (start + (r/8)*SBO + (r%8)*row_bytes) and
+//               applies the swizzle XOR on ABSOLUTE shared-memory address bits, exactly like the TMA unit that wrote
+//               the tile (scripts/experiments/umma_rowshift.cu, verified on B200 for 64B / 128B swizzle, every start
+//               row and group stride tried).  An M tile is therefore 8 pixels wide x 16 rows: its 8-row groups are
+//               8 consecutive pixels of one halo row.  The input is fetched from L2 ONCE per tile (x1.41 halo) instead
+//               of once per filter column (x3.75).  Pixels outside the image are ZERO-FILLED by the TMA unit == the
+//               conv's zero padding (unet.py:29,36).  Rows are CIN_BLK bf16 (64 or 128 bytes) with the matching
+//               64B/128B swizzle: the canonical K-major UMMA layout, no im2col is ever materialised.
 //   B operand   packed weights [tap][kchunk][n][CIN_BLK] bf16, conv_f and conv_m side by side in N so ONE
 //               accumulator tile holds both gates of the same output channels.  When the whole layer fits
 //               (<= 144 KB: the C=32 and C=64 layers) the weights are loaded ONCE per CTA and stay resident in
@@ -34,7 +39,7 @@ namespace rb {
 
 constexpr int TC_THREADS = 384;            // 4 role warps + 8 epilogue warps
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_TW = 16, TC_TH = 8;          // 128-pixel M tile
+constexpr int TC_TW = 8, TC_TH = 16;          // 128-pixel M tile: 16 rows of 8 pixels (one 8-row UMMA group per image row)
 constexpr int TC_MAX_STAGES = 16;           // ring depth bounds the bytes in flight per SM (latency-bound small-C layers)
 constexpr uint32_t TC_SMEM_BUDGET = 218 * 1024;
 constexpr uint32_t TC_RESIDENT_MAX = 144 * 1024;
@@ -51,7 +56,8 @@ struct TcArgs {
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
     int a_stages, b_stages, b_resident;
-    int kxs;                               // filter columns per A ring stage (1, or ksize: tile-granular stages)
+    int halo_w;                            // halo tile width in pixels (TC_TW + ksize - 1)
+    uint32_t a_tx_bytes;                   // bytes one halo-tile load delivers (a_bytes is that rounded up to 1 KB)
     float inv_tx, inv_ty;                  // 1/tiles_x, 1/tiles_y for the division-free tile decode
     int nacc;                              // accumulator ring depth (each n_tile TMEM columns wide)
     int dual;                              // two MMA issuer warps, each with its own half of the A ring (resident weights only)
@@ -111,11 +117,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 // NTHR = 640: 16 epilogue warps, 8-column chunks (Cout <= 64): those layers have so little MMA work per tile (576 / 2304
 //             tensor cycles) that the epilogue's instruction stream bounds them; twice the warps halve each warp's
 //             share and give the schedulers 4 warps per SMSP to hide the MUFU / TMEM / global-load latencies.
-// KXS = filter columns per A ring stage: 1, or KS (one stage = the whole tile's k halo loads; needs resident weights).
-//       Round-1 knob experiments: with ALL work disabled the C=32 kernel still took 1600 cycles per tile - the serial
-//       latency of one producer warp doing 3 x (wait, expect_tx, TMA, ring update) per tile and of the issuers' per-stage
-//       wait / elect / commit.  A tile-granular stage needs one wait, one expect_tx and one commit per tile.
-template <int KS, int KKN, bool RES, int NTHR, int EPI, int KXS>
+// A ring stage = one halo tile (all k x k taps of one K chunk): one wait, one expect_tx, one TMA load and one
+//       tcgen05.commit per tile and K chunk (round-1 knob experiments: with ALL work disabled the C=32 kernel still took
+//       1600 cycles per tile in the serial wait / expect_tx / TMA / commit chains of per-filter-column stages).
+template <int KS, int KKN, bool RES, int NTHR, int EPI>
 __global__ void __launch_bounds__(NTHR, 1)
 gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
@@ -186,7 +191,6 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // single-producer / single-consumer queue, so mbarrier phase parity can never alias
         const uint32_t ring_n = a.dual ? (uint32_t)a.a_stages / 2u : (uint32_t)a.a_stages;
         const uint32_t ring_base = a.dual ? pme * ring_n : 0u;
-        const uint32_t stage_bytes = (uint32_t)KXS * a.a_bytes;
         uint32_t as = 0, aph = 0;
         uint32_t bs = 0, bph = 0, tile_it = 0;
         uint32_t b_addr = b_region;
@@ -202,30 +206,26 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const long long tp = t + pf_dist;
             if (tp < total_tiles && elect_one()) {
                 const TileCoord pc = decode_tile(tp, a);
-                const int ptx_ = pc.tx, pty = pc.ty, pb = pc.b;
                 for (int kc = 0; kc < a.kchunks; ++kc)
-                    tma_prefetch_4d(&tmA, kc * a.cin_blk, ptx_ * TC_TW, pty * TC_TH - a.pad, pb);
+                    tma_prefetch_4d(&tmA, kc * a.cin_blk, pc.tx * TC_TW - a.pad, pc.ty * TC_TH - a.pad, pc.b);
             }
             __syncwarp();
             for (int kc = 0; kc < a.kchunks; ++kc) {
-#pragma unroll
-                for (int kx = 0; kx < KS; kx += KXS) {
-                    const uint32_t slot = ring_base + as;
-                    mbar_wait(aempty0 + 8 * slot, aph ^ 1u);
-                    if (elect_one()) {
-                        if (a.debug & 4) {
-                            mbar_arrive(afull0 + 8 * slot);
-                        } else {
-                            mbar_arrive_expect_tx(afull0 + 8 * slot, stage_bytes);
-#pragma unroll
-                            for (int i = 0; i < KXS; ++i)
-                                tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * stage_bytes + (uint32_t)i * a.a_bytes,
-                                            kc * a.cin_blk, x0 + kx + i, y0, b);
-                        }
+                const uint32_t slot = ring_base + as;
+                mbar_wait(aempty0 + 8 * slot, aph ^ 1u);
+                if (elect_one()) {
+                    if (a.debug & 4) {
+                        mbar_arrive(afull0 + 8 * slot);
+                    } else {
+                        mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_tx_bytes);
+                        tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0, y0, b);
                     }
-                    __syncwarp();
-                    if (++as == ring_n) { as = 0; aph ^= 1u; }
-                    if (!RES) {                                                            // (KXS == 1 here)
+                }
+                __syncwarp();
+                if (++as == ring_n) { as = 0; aph ^= 1u; }
+                if (!RES) {
+#pragma unroll
+                    for (int kx = 0; kx < KS; ++kx) {
                         int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*KS + kx
 #pragma unroll
                         for (int ky = 0; ky < KS; ++ky, row += row_step) {
@@ -252,11 +252,14 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t row_bytes = KKN * 16u * 2u;                 // cin_blk bf16
         constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
-        const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, 8u * row_bytes, layout_type) >> 32);
+        // SBO = stride between consecutive 8-row groups = one halo row (halo_w pixels)
+        const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, (uint32_t)a.halo_w * row_bytes, layout_type) >> 32);
+        const uint32_t desc_hi_b = (uint32_t)(make_kmajor_desc(0, 8u * row_bytes, layout_type) >> 32);   // weights: dense rows
         constexpr uint32_t lo_lbo = 1u << 16;                          // LBO field (ignored for swizzled K-major), kept = 1
-        constexpr uint32_t ky_step = (TC_TW * row_bytes) >> 4;         // one tile row of pixels, in 16-byte units
+        constexpr uint32_t px16 = row_bytes >> 4;                       // one pixel row, in 16-byte units
+        const uint32_t ky_step = (uint32_t)a.halo_w * px16;            // one halo row of pixels
         const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_bytes >> 4;
-        const uint32_t st16 = (uint32_t)KXS * a16;                     // one ring stage, in 16-byte units
+        const uint32_t st16 = a16;                                     // one ring stage, in 16-byte units
         const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
         const uint32_t tap16 = (uint32_t)a.kchunks * b16;              // resident weights: +1 tap
         if (RES) mbar_wait(bres, 0);
@@ -279,46 +282,43 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_tile;
             uint32_t bkc = b_lo0;                                      // resident weights: chunk kc of tap 0
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
+                mbar_wait(afull0 + 8 * (ring_bar + as), aph);
+                tcgen05_fence_after();
 #pragma unroll
-                for (int kxg = 0; kxg < KS; kxg += KXS) {
-                    mbar_wait(afull0 + 8 * (ring_bar + as), aph);
-                    tcgen05_fence_after();
+                for (int kx = 0; kx < KS; ++kx) {
 #pragma unroll
-                    for (int ki = 0; ki < KXS; ++ki) {
-                        const int kx = kxg + ki;
+                    for (int ky = 0; ky < KS; ++ky) {
+                        uint32_t bl;
+                        if (RES) {
+                            bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
+                        } else {
+                            mbar_wait(bfull0 + 8 * bs, bph);
+                            tcgen05_fence_after();
+                            bl = b_lo;
+                        }
+                        // tap (ky, kx): start (ky * halo_w + kx) pixel rows into the halo tile
+                        const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ky = 0; ky < KS; ++ky) {
-                            uint32_t bl;
-                            if (RES) {
-                                bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
-                            } else {
-                                mbar_wait(bfull0 + 8 * bs, bph);
-                                tcgen05_fence_after();
-                                bl = b_lo;
+                            for (int kk = 0; kk < KKN; ++kk) {
+                                if (a.debug & 2) continue;
+                                // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                                const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                                umma_bf16_lohi2(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, accum);
                             }
-                            const uint32_t al = a_lo + (uint32_t)ki * a16 + (uint32_t)ky * ky_step;
-                            if (elect_one()) {
-#pragma unroll
-                                for (int kk = 0; kk < KKN; ++kk) {
-                                    if (a.debug & 2) continue;
-                                    // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                                    const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
-                                    umma_bf16_lohi(d_tmem, al + 2u * kk, bl + 2u * kk, desc_hi, idesc, accum);
-                                }
-                                if (!RES) umma_commit(bempty0 + 8 * bs);
-                            }
-                            __syncwarp();
-                            if (!RES) {
-                                b_lo += b16;
-                                if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
-                            }
+                            if (!RES) umma_commit(bempty0 + 8 * bs);
+                        }
+                        __syncwarp();
+                        if (!RES) {
+                            b_lo += b16;
+                            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
                         }
                     }
-                    if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
-                    __syncwarp();
-                    a_lo += st16;
-                    if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
                 }
+                if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
+                __syncwarp();
+                a_lo += st16;
+                if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
             }
             if (elect_one()) umma_commit(tfull0 + 8 * acc);
             __syncwarp();
@@ -659,12 +659,12 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     TcPlan *p = new (std::nothrow) TcPlan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
 
-    const int halo_rows = TC_TH + d.k - 1;
+    const int halo_rows = TC_TH + d.k - 1, halo_w = TC_TW + d.k - 1;
     const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {   // activations: dims {C, W, H, B}; box = one halo tile for one filter column
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, TC_TW, (cuuint32_t)halo_rows, 1};
+        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, (cuuint32_t)halo_w, (cuuint32_t)halo_rows, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.src[0].ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -696,18 +696,15 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.cin_blk = g.cin_blk; a.kchunks = g.kchunks; a.n_tile = g.n_tile; a.n_tiles = g.n_tiles;
     a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
     a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
-    a.a_bytes = (uint32_t)halo_rows * TC_TW * g.cin_blk * 2u;
+    a.halo_w = halo_w;
+    a.a_tx_bytes = (uint32_t)halo_rows * halo_w * g.cin_blk * 2u;
+    a.a_bytes = (a.a_tx_bytes + 1023u) & ~1023u;       // stages stay 1 KB aligned (swizzle patterns are address based)
     a.b_bytes = (uint32_t)g.n_tile * g.cin_blk * 2u;
     const uint32_t total_b = (uint32_t)(d.k * d.k * g.kchunks) * a.b_bytes;
     a.b_resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b >= 2 * a.a_bytes) ? 1 : 0;
     uint32_t b_region_bytes;
-    a.kxs = 1;
     if (a.b_resident) {
         int st = (int)((TC_SMEM_BUDGET - total_b) / a.a_bytes);
-        if (d.k == 3 && st / 3 >= 4) {        // room for >= 4 whole-tile stages: one wait / expect_tx / commit per tile
-            a.kxs = 3;
-            st /= 3;
-        }
         a.a_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         a.b_stages = 0;
         b_region_bytes = total_b;
@@ -720,9 +717,9 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.inv_tx = 1.0f / (float)a.tiles_x;
     a.inv_ty = 1.0f / (float)a.tiles_y;
     a.nacc = TC_TMEM_COLS / g.n_tile > TC_MAX_ACC ? TC_MAX_ACC : TC_TMEM_COLS / g.n_tile;
-    a.dual = (a.b_resident && a.a_stages >= (a.kxs == 3 ? 4 : 6)) ? 1 : 0;
+    a.dual = (a.b_resident && a.a_stages >= 4 * g.kchunks) ? 1 : 0;      // >= 2 tiles of A per issuer
     if (a.dual) a.a_stages &= ~1;            // two equal half rings
-    a.b_region_off = (uint32_t)a.a_stages * (uint32_t)a.kxs * a.a_bytes;
+    a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
@@ -745,39 +742,36 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
-#define RB_TC_LAUNCH_I(KS_, KKN_, RES_, NT_, EPI_, KXS_)                                                               \
+#define RB_TC_LAUNCH_I(KS_, KKN_, RES_, NT_, EPI_)                                                                     \
     do {                                                                                                                \
-        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, KXS_>,                            \
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_>,                                  \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));                 \
-        gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, KXS_><<<(unsigned)grid, NT_, p->smem_bytes, st>>>(p->tmA, p->tmB, a); \
+        gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_><<<(unsigned)grid, NT_, p->smem_bytes, st>>>(p->tmA, p->tmB, a); \
     } while (0)
-#define RB_TC_LAUNCH(KS_, KKN_, RES_, KXS_)                                                                             \
+#define RB_TC_LAUNCH(KS_, KKN_, RES_)                                                                                   \
     do {                                                                                                                \
-        if (lean) RB_TC_LAUNCH_I(KS_, KKN_, RES_, 640, 0, KXS_);                                                        \
-        else RB_TC_LAUNCH_I(KS_, KKN_, RES_, 384, 0, KXS_);                                                             \
+        if (lean) RB_TC_LAUNCH_I(KS_, KKN_, RES_, 640, 0);                                                              \
+        else RB_TC_LAUNCH_I(KS_, KKN_, RES_, 384, 0);                                                                   \
     } while (0)
-    // lean 16-warp epilogue: Cout 16..64 and 32-bit output offsets
+    // lean 16-warp epilogue: Cout 16 / 32 / 64 and 32-bit output offsets
     const int half_n = a.n_tile >> 1;
     const bool lean = (half_n == 16 || half_n == 32 || half_n == 64) && a.Cout == a.cout_pad &&
                       (long long)a.B * a.H * a.W * a.Cout < (1ll << 31);
     const int kkn = a.cin_blk / 16;
-    const bool ts = a.kxs == 3;             // tile-granular A stages (implies ksize 3 and resident weights)
     // the two ResBlock layer kinds of the C=32 / C=64 stages get compile-time epilogues
     const int epi = (lean && a.ksize == 3 && a.b_resident && !a.out2) ? ((a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0)) : 0;
-    if (epi == 1 && kkn == 2 && ts) RB_TC_LAUNCH_I(3, 2, true, 640, 1, 3);
-    else if (epi == 2 && kkn == 2 && ts) RB_TC_LAUNCH_I(3, 2, true, 640, 2, 3);
-    else if (epi == 1 && kkn == 4 && !ts) RB_TC_LAUNCH_I(3, 4, true, 640, 1, 1);
-    else if (epi == 2 && kkn == 4 && !ts) RB_TC_LAUNCH_I(3, 4, true, 640, 2, 1);
-    else if (a.ksize == 3 && kkn == 4 && a.b_resident && ts) RB_TC_LAUNCH(3, 4, true, 3);
-    else if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true, 1);
-    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false, 1);
-    else if (a.ksize == 3 && kkn == 2 && a.b_resident && ts) RB_TC_LAUNCH(3, 2, true, 3);
-    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true, 1);
-    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false, 1);
-    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true, 1);
-    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false, 1);
-    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true, 1);
-    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false, 1);
+    if (epi == 1 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 1);
+    else if (epi == 2 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 2);
+    else if (epi == 1 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 1);
+    else if (epi == 2 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 2);
+    else if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true);
+    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false);
+    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true);
+    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false);
+    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true);
+    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false);
+    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true);
+    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false);
     else {
         set_error("tcgen05 conv: no kernel instance for k=%d cin_blk=%d", a.ksize, a.cin_blk);
         return READ_ERR_UNSUPPORTED;

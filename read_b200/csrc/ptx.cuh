@@ -138,6 +138,22 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, ui
         "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with separate hi halves for A and B (different 8-row-group strides)
+__device__ __forceinline__ void umma_bf16_lohi2(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                                uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 // mbarrier arrives once all tcgen05.mma previously issued by this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
