@@ -284,39 +284,54 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
                 mbar_wait(afull0 + 8 * (ring_bar + as), aph);
                 tcgen05_fence_after();
+                if (RES) {
+                    // resident weights: nothing to wait for between taps - ONE elected block issues the whole stage
+                    // (k*k*KKN MMAs + the commit) instead of an elect / syncwarp pair per tap
+                    if (elect_one()) {
 #pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
+                        for (int kx = 0; kx < KS; ++kx) {
 #pragma unroll
-                    for (int ky = 0; ky < KS; ++ky) {
-                        uint32_t bl;
-                        if (RES) {
-                            bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
-                        } else {
+                            for (int ky = 0; ky < KS; ++ky) {
+                                const uint32_t bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
+                                const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;   // tap (ky, kx)
+#pragma unroll
+                                for (int kk = 0; kk < KKN; ++kk) {
+                                    if (a.debug & 2) continue;
+                                    const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                                    umma_bf16_lohi2(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, accum);
+                                }
+                            }
+                        }
+                        umma_commit(aempty0 + 8 * (ring_bar + as));
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll
+                        for (int ky = 0; ky < KS; ++ky) {
                             mbar_wait(bfull0 + 8 * bs, bph);
                             tcgen05_fence_after();
-                            bl = b_lo;
-                        }
-                        // tap (ky, kx): start (ky * halo_w + kx) pixel rows into the halo tile
-                        const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
-                        if (elect_one()) {
+                            // tap (ky, kx): start (ky * halo_w + kx) pixel rows into the halo tile
+                            const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
+                            if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < KKN; ++kk) {
-                                if (a.debug & 2) continue;
-                                // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                                const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
-                                umma_bf16_lohi2(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, accum);
+                                for (int kk = 0; kk < KKN; ++kk) {
+                                    if (a.debug & 2) continue;
+                                    // +16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                                    const uint32_t accum = (kx | ky | kk) != 0 ? 1u : (kc != 0 ? 1u : 0u);
+                                    umma_bf16_lohi2(d_tmem, al + 2u * kk, desc_hi, b_lo + 2u * kk, desc_hi_b, idesc, accum);
+                                }
+                                umma_commit(bempty0 + 8 * bs);
                             }
-                            if (!RES) umma_commit(bempty0 + 8 * bs);
-                        }
-                        __syncwarp();
-                        if (!RES) {
+                            __syncwarp();
                             b_lo += b16;
                             if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1u; b_lo = b_lo0; }
                         }
                     }
+                    if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
+                    __syncwarp();
                 }
-                if (elect_one()) umma_commit(aempty0 + 8 * (ring_bar + as));
-                __syncwarp();
                 a_lo += st16;
                 if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
             }
