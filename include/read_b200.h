@@ -177,6 +177,10 @@ int read_generic_npad(int Cout);
 int read_pack_weights_generic(const float *wf, const float *wm, int Cout, int Cin, int k, float *out,
                               void *stream);
 int64_t read_tc_weight_elems(int Cout, int Cin, int k);
+/* K-chunking of the packed layout depends on the conv stride (32-channel chunks for stride 2): pack with the stride the
+ * plan will be created with.  read_pack_weights_tc == stride 1. */
+int read_pack_weights_tc_strided(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, void *out_bf16,
+                                 void *stream);
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16,
                          void *stream);
 /* 1 if the tcgen05 TMA kernel (stride-1, single source) supports this layer, else 0. */

@@ -56,8 +56,10 @@ struct TcArgs {
     int n_tile, n_tiles;
     int tiles_x, tiles_y;
     int a_stages, b_stages, b_resident;
-    int halo_w;                            // halo tile width in pixels (TC_TW + ksize - 1)
-    uint32_t a_tx_bytes;                   // bytes one halo-tile load delivers (a_bytes is that rounded up to 1 KB)
+    int halo_w;                            // smem tile width in pixels: TC_TW + ksize - 1 (stride 1) or TC_TW + 1 (stride 2)
+    uint32_t a_tx_bytes;                   // bytes one tile load delivers
+    uint32_t tile_bytes;                   // that rounded up to 1 KB; a_bytes = tile_bytes (stride 1) or 4 x tile_bytes (stride 2)
+    int stride;                            // 1, or 2: four phase tiles (even / odd input columns x rows) per stage
     float inv_tx, inv_ty;                  // 1/tiles_x, 1/tiles_y for the division-free tile decode
     int nacc;                              // accumulator ring depth (each n_tile TMEM columns wide)
     int dual;                              // two MMA issuer warps, each with its own half of the A ring (resident weights only)
@@ -120,7 +122,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 // A ring stage = one halo tile (all k x k taps of one K chunk): one wait, one expect_tx, one TMA load and one
 //       tcgen05.commit per tile and K chunk (round-1 knob experiments: with ALL work disabled the C=32 kernel still took
 //       1600 cycles per tile in the serial wait / expect_tx / TMA / commit chains of per-filter-column stages).
-template <int KS, int KKN, bool RES, int NTHR, int EPI>
+// STR = conv stride.  STR == 2 (3x3 / 4x4, pad 1): input column 2x + kx - 1 is an EVEN column for kx odd and an ODD one for kx
+//       even, so a stage holds four phase tiles E/O x E/O, each loaded by one TMA with traversal stride 2 in x and y
+//       (tile[j][i] = in(sx + 2i, sy + 2j), sx = 2*X0 for E, 2*X0 - 1 for O); tap (ky, kx) reads phase tile
+//       ((ky+1)&1, (kx+1)&1) at pixel offset (ky>>1, kx>>1) through the same row-linear descriptors.
+template <int KS, int KKN, bool RES, int NTHR, int EPI, int STR>
 __global__ void __launch_bounds__(NTHR, 1)
 gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
@@ -204,7 +210,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // warm L2 with the halo tile this producer will need two of its tiles from now (DRAM latency is what bounds
             // the small-C layers: the ring can only keep a_stages * a_bytes in flight per SM)
             const long long tp = t + pf_dist;
-            if (tp < total_tiles && elect_one()) {
+            if (STR == 1 && tp < total_tiles && elect_one()) {
                 const TileCoord pc = decode_tile(tp, a);
                 for (int kc = 0; kc < a.kchunks; ++kc)
                     tma_prefetch_4d(&tmA, kc * a.cin_blk, pc.tx * TC_TW - a.pad, pc.ty * TC_TH - a.pad, pc.b);
@@ -217,8 +223,17 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (a.debug & 4) {
                         mbar_arrive(afull0 + 8 * slot);
                     } else {
-                        mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_tx_bytes);
-                        tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0, y0, b);
+                        if (STR == 1) {
+                            mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_tx_bytes);
+                            tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0, y0, b);
+                        } else {
+                            mbar_arrive_expect_tx(afull0 + 8 * slot, 4u * a.a_tx_bytes);
+                            const int ex = 2 * tx * TC_TW, ey = 2 * ty * TC_TH;        // even-phase origin in the input
+#pragma unroll
+                            for (int ph4 = 0; ph4 < 4; ++ph4)
+                                tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes + (uint32_t)ph4 * a.tile_bytes,
+                                            kc * a.cin_blk, ex - (ph4 & 1), ey - (ph4 >> 1), b);
+                        }
                     }
                 }
                 __syncwarp();
@@ -258,7 +273,12 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t lo_lbo = 1u << 16;                          // LBO field (ignored for swizzled K-major), kept = 1
         constexpr uint32_t px16 = row_bytes >> 4;                       // one pixel row, in 16-byte units
         const uint32_t ky_step = (uint32_t)a.halo_w * px16;            // one halo row of pixels
-        const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_bytes >> 4;
+        const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_bytes >> 4, tile16 = a.tile_bytes >> 4;
+        // tap (ky, kx) -> 16-byte offset of its A rows inside the stage
+        auto tap_off = [&](int ky, int kx) -> uint32_t {
+            if (STR == 1) return (uint32_t)ky * ky_step + (uint32_t)kx * px16;
+            return (uint32_t)((((ky + 1) & 1) << 1) | ((kx + 1) & 1)) * tile16 + (uint32_t)(ky >> 1) * ky_step + (uint32_t)(kx >> 1) * px16;
+        };
         const uint32_t st16 = a16;                                     // one ring stage, in 16-byte units
         const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
         const uint32_t tap16 = (uint32_t)a.kchunks * b16;              // resident weights: +1 tap
@@ -293,7 +313,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int ky = 0; ky < KS; ++ky) {
                                 const uint32_t bl = bkc + (uint32_t)(ky * KS + kx) * tap16;
-                                const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;   // tap (ky, kx)
+                                const uint32_t al = a_lo + tap_off(ky, kx);
 #pragma unroll
                                 for (int kk = 0; kk < KKN; ++kk) {
                                     if (a.debug & 2) continue;
@@ -312,8 +332,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int ky = 0; ky < KS; ++ky) {
                             mbar_wait(bfull0 + 8 * bs, bph);
                             tcgen05_fence_after();
-                            // tap (ky, kx): start (ky * halo_w + kx) pixel rows into the halo tile
-                            const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
+                            const uint32_t al = a_lo + tap_off(ky, kx);
                             if (elect_one()) {
 #pragma unroll
                                 for (int kk = 0; kk < KKN; ++kk) {
@@ -600,10 +619,11 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
 struct TcGeom {
     int cin_blk, kchunks, n_tile, n_tiles, cout_pad;
 };
-static bool tc_geom(int Cin, int Cout, TcGeom *g)
+static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g)
 {
     int cin_blk;
-    if (Cin % 64 == 0) cin_blk = 64;
+    // stride 2 keeps four phase tiles per stage: 32-channel K chunks keep a 3-stage ring within shared memory
+    if (Cin % 64 == 0 && stride == 1) cin_blk = 64;
     else if (Cin % 32 == 0) cin_blk = 32;
     else return false;
     int cout_pad = Cout;
@@ -621,15 +641,21 @@ bool tc_supported(const read_conv_desc &d)
 {
     if (d.act_dtype != READ_ACT_BF16) return false;
     if (d.n_src != 1 || d.src[0].mode != READ_SRC_IDENTITY || d.mul != nullptr) return false;
-    if (d.stride != 1 || !(d.k == 3 || d.k == 1)) return false;
-    if (d.pad != (d.k - 1) / 2) return false;
-    if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+    if (d.stride == 1) {
+        if (!(d.k == 3 || d.k == 1) || d.pad != (d.k - 1) / 2) return false;
+        if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+    } else if (d.stride == 2) {            // 3x3 / 4x4, pad 1, even input: four phase tiles (see the kernel)
+        if (!(d.k == 3 || d.k == 4) || d.pad != 1) return false;
+        if (d.Hin != 2 * d.Hout || d.Win != 2 * d.Wout) return false;
+    } else {
+        return false;
+    }
     if (d.Cout <= 8) {
         if (d.out_mode != READ_OUT_NCHW_F32 || d.residual || d.out2) return false;   // final layer only
     } else if (d.out_mode != READ_OUT_NHWC) {
         return false;
     }
-    return tc_geom(d.Cin, d.Cout, nullptr);
+    return tc_geom(d.Cin, d.Cout, d.stride, nullptr);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -659,7 +685,7 @@ struct TcPlan {
 int tc_plan_create(const read_conv_desc &d, TcPlan **out)
 {
     TcGeom g;
-    if (!tc_supported(d) || !tc_geom(d.Cin, d.Cout, &g)) {
+    if (!tc_supported(d) || !tc_geom(d.Cin, d.Cout, d.stride, &g)) {
         set_error("tcgen05 conv: unsupported layer");
         return READ_ERR_UNSUPPORTED;
     }
@@ -674,13 +700,16 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     TcPlan *p = new (std::nothrow) TcPlan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
 
-    const int halo_rows = TC_TH + d.k - 1, halo_w = TC_TW + d.k - 1;
+    const bool s2 = d.stride == 2;
+    const int halo_rows = s2 ? TC_TH + 1 : TC_TH + d.k - 1, halo_w = s2 ? TC_TW + 1 : TC_TW + d.k - 1;
     const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {   // activations: dims {C, W, H, B}; box = one halo tile for one filter column
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, (cuuint32_t)halo_w, (cuuint32_t)halo_rows, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        // stride 2: traversal stride 2 in x and y; the box spans 2n-1 input elements and delivers n of them
+        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, (cuuint32_t)(s2 ? 2 * halo_w - 1 : halo_w),
+                             (cuuint32_t)(s2 ? 2 * halo_rows - 1 : halo_rows), 1};
+        cuuint32_t estr[4] = {1, s2 ? 2u : 1u, s2 ? 2u : 1u, 1};
         CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.src[0].ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -712,8 +741,10 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
     a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
     a.halo_w = halo_w;
+    a.stride = d.stride;
     a.a_tx_bytes = (uint32_t)halo_rows * halo_w * g.cin_blk * 2u;
-    a.a_bytes = (a.a_tx_bytes + 1023u) & ~1023u;       // stages stay 1 KB aligned (swizzle patterns are address based)
+    a.tile_bytes = (a.a_tx_bytes + 1023u) & ~1023u;    // tiles stay 1 KB aligned (swizzle patterns are address based)
+    a.a_bytes = s2 ? 4u * a.tile_bytes : a.tile_bytes;
     a.b_bytes = (uint32_t)g.n_tile * g.cin_blk * 2u;
     const uint32_t total_b = (uint32_t)(d.k * d.k * g.kchunks) * a.b_bytes;
     a.b_resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b >= 2 * a.a_bytes) ? 1 : 0;
@@ -725,6 +756,11 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         b_region_bytes = total_b;
     } else {
         a.a_stages = 3;
+        if (3 * a.a_bytes + 2 * a.b_bytes > TC_SMEM_BUDGET) {
+            set_error("tcgen05 conv: layer does not fit shared memory (A stage %u B, B tile %u B)", a.a_bytes, a.b_bytes);
+            delete p;
+            return READ_ERR_UNSUPPORTED;
+        }
         int st = (int)((TC_SMEM_BUDGET - 3 * a.a_bytes) / a.b_bytes);
         a.b_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         b_region_bytes = (uint32_t)a.b_stages * a.b_bytes;
@@ -757,16 +793,23 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
-#define RB_TC_LAUNCH_I(KS_, KKN_, RES_, NT_, EPI_)                                                                     \
+#define RB_TC_LAUNCH_I(KS_, KKN_, RES_, NT_, EPI_, STR_)                                                               \
     do {                                                                                                                \
-        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_>,                                  \
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, STR_>,                            \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));                 \
-        gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_><<<(unsigned)grid, NT_, p->smem_bytes, st>>>(p->tmA, p->tmB, a); \
+        gated_conv_tc_kernel<KS_, KKN_, RES_, NT_, EPI_, STR_><<<(unsigned)grid, NT_, p->smem_bytes, st>>>(p->tmA, p->tmB, a); \
     } while (0)
-#define RB_TC_LAUNCH(KS_, KKN_, RES_)                                                                                   \
+#define RB_TC_LAUNCH(KS_, KKN_, RES_, STR_)                                                                             \
     do {                                                                                                                \
-        if (lean) RB_TC_LAUNCH_I(KS_, KKN_, RES_, 640, 0);                                                              \
-        else RB_TC_LAUNCH_I(KS_, KKN_, RES_, 384, 0);                                                                   \
+        if (lean) RB_TC_LAUNCH_I(KS_, KKN_, RES_, 640, 0, STR_);                                                        \
+        else RB_TC_LAUNCH_I(KS_, KKN_, RES_, 384, 0, STR_);                                                             \
+    } while (0)
+#define RB_TC_LAUNCH_K(KS_, STR_)                                                                                       \
+    do {                                                                                                                \
+        if (kkn == 4 && a.b_resident) RB_TC_LAUNCH(KS_, 4, true, STR_);                                                 \
+        else if (kkn == 4) RB_TC_LAUNCH(KS_, 4, false, STR_);                                                           \
+        else if (a.b_resident) RB_TC_LAUNCH(KS_, 2, true, STR_);                                                        \
+        else RB_TC_LAUNCH(KS_, 2, false, STR_);                                                                         \
     } while (0)
     // lean 16-warp epilogue: Cout 16 / 32 / 64 and 32-bit output offsets
     const int half_n = a.n_tile >> 1;
@@ -774,23 +817,25 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
                       (long long)a.B * a.H * a.W * a.Cout < (1ll << 31);
     const int kkn = a.cin_blk / 16;
     // the two ResBlock layer kinds of the C=32 / C=64 stages get compile-time epilogues
-    const int epi = (lean && a.ksize == 3 && a.b_resident && !a.out2) ? ((a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0)) : 0;
-    if (epi == 1 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 1);
-    else if (epi == 2 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 2);
-    else if (epi == 1 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 1);
-    else if (epi == 2 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 2);
-    else if (a.ksize == 3 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(3, 4, true);
-    else if (a.ksize == 3 && kkn == 4) RB_TC_LAUNCH(3, 4, false);
-    else if (a.ksize == 3 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(3, 2, true);
-    else if (a.ksize == 3 && kkn == 2) RB_TC_LAUNCH(3, 2, false);
-    else if (a.ksize == 1 && kkn == 4 && a.b_resident) RB_TC_LAUNCH(1, 4, true);
-    else if (a.ksize == 1 && kkn == 4) RB_TC_LAUNCH(1, 4, false);
-    else if (a.ksize == 1 && kkn == 2 && a.b_resident) RB_TC_LAUNCH(1, 2, true);
-    else if (a.ksize == 1 && kkn == 2) RB_TC_LAUNCH(1, 2, false);
-    else {
-        set_error("tcgen05 conv: no kernel instance for k=%d cin_blk=%d", a.ksize, a.cin_blk);
+    const int epi = (lean && a.stride == 1 && a.ksize == 3 && a.b_resident && !a.out2)
+                        ? ((a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0)) : 0;
+    if (kkn != 2 && kkn != 4) {
+        set_error("tcgen05 conv: no kernel instance for cin_blk=%d", a.cin_blk);
         return READ_ERR_UNSUPPORTED;
     }
+    if (epi == 1 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 1, 1);
+    else if (epi == 2 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 2, 1);
+    else if (epi == 1 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 1, 1);
+    else if (epi == 2 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 2, 1);
+    else if (a.stride == 1 && a.ksize == 3) RB_TC_LAUNCH_K(3, 1);
+    else if (a.stride == 1 && a.ksize == 1) RB_TC_LAUNCH_K(1, 1);
+    else if (a.stride == 2 && a.ksize == 3 && kkn == 2) { if (a.b_resident) RB_TC_LAUNCH(3, 2, true, 2); else RB_TC_LAUNCH(3, 2, false, 2); }
+    else if (a.stride == 2 && a.ksize == 4 && kkn == 2) { if (a.b_resident) RB_TC_LAUNCH(4, 2, true, 2); else RB_TC_LAUNCH(4, 2, false, 2); }
+    else {
+        set_error("tcgen05 conv: no kernel instance for k=%d stride=%d", a.ksize, a.stride);
+        return READ_ERR_UNSUPPORTED;
+    }
+#undef RB_TC_LAUNCH_K
 #undef RB_TC_LAUNCH_I
 #undef RB_TC_LAUNCH
     RB_LAUNCH_CHECK();
@@ -808,15 +853,22 @@ extern "C" {
 int64_t read_tc_weight_elems(int Cout, int Cin, int k)
 {
     TcGeom g;
-    if (!tc_geom(Cin, Cout, &g)) return -1;
+    if (!tc_geom(Cin, Cout, 1, &g)) return -1;
     return (int64_t)k * k * Cin * 2 * g.cout_pad;
 }
 
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream)
 {
+    return read_pack_weights_tc_strided(wf, wm, Cout, Cin, k, 1, out_bf16, stream);
+}
+
+int read_pack_weights_tc_strided(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, void *out_bf16,
+                                 void *stream)
+{
     TcGeom g;
     RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc: null pointer");
-    RB_CHECK_ARG(tc_geom(Cin, Cout, &g), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
+    RB_CHECK_ARG(stride == 1 || stride == 2, "pack_tc: stride must be 1 or 2");
+    RB_CHECK_ARG(tc_geom(Cin, Cout, stride, &g), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
     const long long total = (long long)k * k * Cin * 2 * g.cout_pad;
     long long blocks = (total + 255) / 256;
     if (blocks > 65535) blocks = 65535;

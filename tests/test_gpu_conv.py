@@ -85,7 +85,7 @@ def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=Fa
     stream = L.stream_ptr()
     if impl == L.CONV_TCGEN05:
         wt = torch.empty(lib.read_tc_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=d)
-        L.check(lib.read_pack_weights_tc(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, wt.data_ptr(), stream))
+        L.check(lib.read_pack_weights_tc_strided(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, stride, wt.data_ptr(), stream))
         dsc.w_tc = wt.data_ptr()
         keep.append(wt)
     elif impl == L.CONV_TCGEN05_GATHER:
@@ -181,13 +181,21 @@ TC_CASES = [
     ("persistent C32, 2560 tiles (17 per CTA)", [(32, 512, 640, "id", 1)], 32, 3, True, {}),
     ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
     ("final layer 32->3, NCHW f32 output", [(32, 24, 40, "id", 1)], 3, 3, False, {"final": True}),
+    # stride 2 on the TMA path: four phase tiles per stage (even / odd input columns x rows), traversal-stride-2 TMA loads
+    ("3x3 s2 32->64 + FAM product output (feat_extract.1)", [(32, 32, 48, "id", 1)], 64, 3, True, {"stride": 2, "out2": True}),
+    ("3x3 s2 64->128 ragged tiles (feat_extract.2)", [(64, 38, 26, "id", 1)], 128, 3, True, {"stride": 2, "out2": True}),
+    ("3x3 s2 128->256, two n-tiles, four k-chunks (feat_extract.6)", [(128, 32, 32, "id", 1)], 256, 3, True, {"stride": 2}),
+    ("4x4 s2 256->128 (feat_extract.7)", [(256, 32, 16, "id", 1)], 128, 4, True, {"stride": 2}),
+    ("4x4 s2 64->32 (feat_extract.4)", [(64, 64, 48, "id", 1)], 32, 4, True, {"stride": 2}),
+    ("3x3 s2 persistent, 1200 tiles", [(32, 640, 960, "id", 1)], 64, 3, True, {"stride": 2}),
 ]
 
 
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_tcgen05_matches_torch(case):
     _, srcs, cout, k, elu, kw = case
-    r = run_conv(srcs, cout, k, 1, elu, True, TC, **kw)
+    kw = dict(kw)
+    r = run_conv(srcs, cout, k, kw.pop("stride", 1), elu, True, TC, **kw)
     got, want = r[0], r[1]
     assert torch.isfinite(got).all(), "tcgen05 kernel left outputs unwritten (NaN sentinel)"
     # bf16 operands are exact in the reference (weights/inputs pre-rounded), accumulation fp32 on both sides:
