@@ -181,9 +181,13 @@ int64_t read_tc_weight_elems(int Cout, int Cin, int k);
  * plan will be created with.  read_pack_weights_tc == stride 1. */
 int read_pack_weights_tc_strided(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, void *out_bf16,
                                  void *stream);
+/* Same, geometry taken from the layer descriptor (stride AND the channel granularity of a virtual concat's sources):
+ * the form a caller should use for any descriptor that read_conv_tc_supported accepts. */
+int read_pack_weights_tc_for(const read_conv_desc *d, const float *wf, const float *wm, void *out_bf16, void *stream);
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16,
                          void *stream);
-/* 1 if the tcgen05 TMA kernel (stride-1, single source) supports this layer, else 0. */
+/* 1 if the tcgen05 TMA kernel supports this layer (stride-1 k x k / stride-2 3x3, 4x4 single source; 1x1 virtual concat of
+ * identity / nearest-down sources), else 0. */
 int read_conv_tc_supported(const read_conv_desc *d);
 /* Same for the tcgen05 kernel with a gathered A operand (any stride / concat / resampling, bf16 activations);
  * it has its own weight packing. */
@@ -201,6 +205,10 @@ void read_conv_plan_destroy(read_conv_plan *p);
 int read_upsample_bilinear4(const void *in, int act_dtype, int B, int h, int w, int C, void *out, void *stream);
 
 /* Layout converters at the net boundary. */
+/* Viewer output path (replaces READ/gl/nn.py:123-124 `permute + cat alpha` and the flip of viewer.py:267):
+ * RGB planes [3,H,W] f32 -> [H,W,4] f32 (alpha constant), optionally flipped vertically. */
+int read_frame_to_rgba(const float *rgb_planes, int H, int W, int flip_vertical, float alpha, float *out_hwc4, void *stream);
+
 int read_nchw_f32_to_nhwc(const float *in, int B, int C, int H, int W, int act_dtype, void *out, void *stream);
 int read_nhwc_to_nchw_f32(const void *in, int act_dtype, int B, int C, int H, int W, float *out, void *stream);
 

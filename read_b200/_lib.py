@@ -69,6 +69,7 @@ _SIGS = {
     "read_tc_weight_elems": (c_i64, [c_int, c_int, c_int]),
     "read_pack_weights_tc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_pack_weights_tc_strided": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_pack_weights_tc_for": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "read_conv_tc_supported": (c_int, [ctypes.POINTER(ReadConvDesc)]),
     "read_conv_tcg_supported": (c_int, [ctypes.POINTER(ReadConvDesc)]),
     "read_tcg_weight_elems": (c_i64, [c_int, c_int, c_int]),
@@ -78,6 +79,7 @@ _SIGS = {
     "read_conv_plan_impl": (c_int, [c_vp]),
     "read_conv_plan_destroy": (None, [c_vp]),
     "read_upsample_bilinear4": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_frame_to_rgba": (c_int, [c_vp, c_int, c_int, c_int, ctypes.c_float, c_vp, c_vp]),
     "read_nchw_f32_to_nhwc": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_nhwc_to_nchw_f32": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_launch_count": (c_i64, []),

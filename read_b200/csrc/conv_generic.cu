@@ -353,6 +353,19 @@ int launch_generic(const read_conv_desc &d, cudaStream_t st)
 
 using namespace rb;
 
+// Viewer output path (READ/gl/nn.py:123-124, viewer.py:267): RGB planes [3,H,W] f32 -> [H,W,4] f32 with alpha, optionally
+// flipped vertically.  One float4 store per pixel, three coalesced plane reads.
+__global__ void frame_to_rgba_kernel(const float *__restrict__ in, int H, int W, int flip, float alpha, float4 *__restrict__ out)
+{
+    const long long n = (long long)H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+        const int ys = flip ? (H - 1 - y) : y;
+        const long long o = (long long)ys * W + x;
+        out[i] = make_float4(in[o], in[n + o], in[2 * n + o], alpha);
+    }
+}
+
 extern "C" {
 
 int read_generic_npad(int Cout) { return generic_npad(Cout); }
@@ -381,6 +394,20 @@ int read_upsample_bilinear4(const void *in, int act_dtype, int B, int h, int w, 
     else
         upsample_bilinear4_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16 *)in, B, h, w, C, (__nv_bfloat16 *)out);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+int read_frame_to_rgba(const float *rgb_planes, int H, int W, int flip_vertical, float alpha, float *out_hwc4, void *stream)
+{
+    RB_CHECK_ARG(rgb_planes && out_hwc4 && H >= 0 && W >= 0, "frame_to_rgba: bad arguments");
+    RB_CHECK_ARG((reinterpret_cast<uintptr_t>(out_hwc4) & 15) == 0, "frame_to_rgba: output must be 16-byte aligned");
+    const long long n = (long long)H * W;
+    if (n == 0) return READ_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    frame_to_rgba_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rgb_planes, H, W, flip_vertical, alpha,
+                                                                             reinterpret_cast<float4 *>(out_hwc4));
     RB_LAUNCH_CHECK();
     return READ_OK;
 }

@@ -49,6 +49,12 @@ constexpr int TC_MAX_ACC = 8;               // TMEM accumulator ring: 512 column
 constexpr int BAR_AFULL = 0, BAR_AEMPTY = 16, BAR_BFULL = 32, BAR_BEMPTY = 48, BAR_TFULL = 64, BAR_TEMPTY = 72,
               BAR_BRES = 80, BAR_TMEMPTR = 82, BAR_PARAMS = 84;
 
+// activation tensor maps: one per source of a virtual concat (1x1 convs: torch.cat along channels, unet.py:88,105,263;
+// a nearest-DOWN resampled source is a traversal-stride load of the full-resolution tensor)
+struct TcMaps {
+    CUtensorMap a[READ_MAX_SRC];
+};
+
 struct TcArgs {
     int B, H, W, Cin, Cout, cout_pad;     // cout_pad > Cout only for the final (Cout <= 8, NCHW f32) layer
     int ksize, pad;
@@ -60,6 +66,9 @@ struct TcArgs {
     uint32_t a_tx_bytes;                   // bytes one tile load delivers
     uint32_t tile_bytes;                   // that rounded up to 1 KB; a_bytes = tile_bytes (stride 1) or 4 x tile_bytes (stride 2)
     int stride;                            // 1, or 2: four phase tiles (even / odd input columns x rows) per stage
+    int n_src;                             // sources of the virtual concat (> 1 only for 1x1 convs)
+    int src_kc_end[READ_MAX_SRC];          // K chunks [src_kc_end[s-1], src_kc_end[s]) come from source s
+    int src_shift[READ_MAX_SRC];           // log2 of the source's nearest-down factor (coordinate multiplier)
     float inv_tx, inv_ty;                  // 1/tiles_x, 1/tiles_y for the division-free tile decode
     int nacc;                              // accumulator ring depth (each n_tile TMEM columns wide)
     int dual;                              // two MMA issuer warps, each with its own half of the A ring (resident weights only)
@@ -128,7 +137,7 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u)
 //       ((ky+1)&1, (kx+1)&1) at pixel offset (ky>>1, kx>>1) through the same row-linear descriptors.
 template <int KS, int KKN, bool RES, int NTHR, int EPI, int STR>
 __global__ void __launch_bounds__(NTHR, 1)
-gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ TcArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -156,7 +165,7 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
+        for (int i = 0; i < a.n_src; ++i) tma_prefetch_desc(&tm.a[i]);
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
@@ -210,10 +219,10 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // warm L2 with the halo tile this producer will need two of its tiles from now (DRAM latency is what bounds
             // the small-C layers: the ring can only keep a_stages * a_bytes in flight per SM)
             const long long tp = t + pf_dist;
-            if (STR == 1 && tp < total_tiles && elect_one()) {
+            if (STR == 1 && a.n_src == 1 && tp < total_tiles && elect_one()) {
                 const TileCoord pc = decode_tile(tp, a);
                 for (int kc = 0; kc < a.kchunks; ++kc)
-                    tma_prefetch_4d(&tmA, kc * a.cin_blk, pc.tx * TC_TW - a.pad, pc.ty * TC_TH - a.pad, pc.b);
+                    tma_prefetch_4d(&tm.a[0], kc * a.cin_blk, pc.tx * TC_TW - a.pad, pc.ty * TC_TH - a.pad, pc.b);
             }
             __syncwarp();
             for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -225,13 +234,24 @@ gated_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     } else {
                         if (STR == 1) {
                             mbar_arrive_expect_tx(afull0 + 8 * slot, a.a_tx_bytes);
-                            tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0, y0, b);
+                            if (a.n_src == 1) {
+                                tma_load_4d(&tm.a[0], afull0 + 8 * slot, smem_base + slot * a.a_bytes, kc * a.cin_blk, x0, y0, b);
+                            } else {
+                                // virtual concat (1x1, pad 0): chunk kc belongs to source si; a down-sampled source is read
+                                // with traversal stride 2^shift from coordinate (x0, y0) << shift
+                                int si = 0, kc0 = 0;
+                                for (int q = 0; q < READ_MAX_SRC - 1; ++q)
+                                    if (q + 1 < a.n_src && kc >= a.src_kc_end[q]) { si = q + 1; kc0 = a.src_kc_end[q]; }
+                                const int sh = a.src_shift[si];
+                                tma_load_4d(&tm.a[si], afull0 + 8 * slot, smem_base + slot * a.a_bytes, (kc - kc0) * a.cin_blk,
+                                            x0 << sh, y0 << sh, b);
+                            }
                         } else {
                             mbar_arrive_expect_tx(afull0 + 8 * slot, 4u * a.a_tx_bytes);
                             const int ex = 2 * tx * TC_TW, ey = 2 * ty * TC_TH;        // even-phase origin in the input
 #pragma unroll
                             for (int ph4 = 0; ph4 < 4; ++ph4)
-                                tma_load_4d(&tmA, afull0 + 8 * slot, smem_base + slot * a.a_bytes + (uint32_t)ph4 * a.tile_bytes,
+                                tma_load_4d(&tm.a[0], afull0 + 8 * slot, smem_base + slot * a.a_bytes + (uint32_t)ph4 * a.tile_bytes,
                                             kc * a.cin_blk, ex - (ph4 & 1), ey - (ph4 >> 1), b);
                         }
                     }
@@ -619,11 +639,20 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
 struct TcGeom {
     int cin_blk, kchunks, n_tile, n_tiles, cout_pad;
 };
-static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g)
+// K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
+static int desc_chan_gran(const read_conv_desc &d)
+{
+    int gsrc = d.Cin;
+    for (int i = 0; i < d.n_src && d.n_src > 1; ++i)
+        if (d.src[i].C % 64 != 0) gsrc = 32;
+    return gsrc;
+}
+
+static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g, int chan_gran = 64)
 {
     int cin_blk;
     // stride 2 keeps four phase tiles per stage: 32-channel K chunks keep a 3-stage ring within shared memory
-    if (Cin % 64 == 0 && stride == 1) cin_blk = 64;
+    if (Cin % 64 == 0 && stride == 1 && chan_gran % 64 == 0) cin_blk = 64;
     else if (Cin % 32 == 0) cin_blk = 32;
     else return false;
     int cout_pad = Cout;
@@ -640,7 +669,25 @@ static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g)
 bool tc_supported(const read_conv_desc &d)
 {
     if (d.act_dtype != READ_ACT_BF16) return false;
-    if (d.n_src != 1 || d.src[0].mode != READ_SRC_IDENTITY || d.mul != nullptr) return false;
+    if (d.mul != nullptr || d.n_src < 1 || d.n_src > READ_MAX_SRC) return false;
+    if (d.n_src == 1) {
+        if (d.src[0].mode != READ_SRC_IDENTITY) return false;
+    } else {
+        // virtual concat: 1x1 convs whose sources are identity or nearest-DOWN by a power of two, 32-channel granular
+        if (d.k != 1 || d.stride != 1) return false;
+        int csum = 0;
+        for (int i = 0; i < d.n_src; ++i) {
+            const read_src &sv = d.src[i];
+            if (sv.mode == READ_SRC_NEAREST_DOWN) {
+                if (sv.factor < 2 || (sv.factor & (sv.factor - 1)) != 0) return false;
+            } else if (sv.mode != READ_SRC_IDENTITY) {
+                return false;
+            }
+            if (sv.C % 32 != 0) return false;
+            csum += sv.C;
+        }
+        if (csum != d.Cin) return false;
+    }
     if (d.stride == 1) {
         if (!(d.k == 3 || d.k == 1) || d.pad != (d.k - 1) / 2) return false;
         if (d.Hin != d.Hout || d.Win != d.Wout) return false;
@@ -655,7 +702,11 @@ bool tc_supported(const read_conv_desc &d)
     } else if (d.out_mode != READ_OUT_NHWC) {
         return false;
     }
-    return tc_geom(d.Cin, d.Cout, d.stride, nullptr);
+    TcGeom g;
+    if (!tc_geom(d.Cin, d.Cout, d.stride, &g, desc_chan_gran(d))) return false;
+    for (int i = 0; i < d.n_src && d.n_src > 1; ++i)
+        if (d.src[i].C % g.cin_blk != 0) return false;       // K chunks may not straddle two sources
+    return true;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -677,7 +728,8 @@ PFN_encodeTiled get_encode_tiled()
 }
 
 struct TcPlan {
-    CUtensorMap tmA, tmB;
+    TcMaps tmA;
+    CUtensorMap tmB;
     TcArgs args;
     size_t smem_bytes;
 };
@@ -685,7 +737,7 @@ struct TcPlan {
 int tc_plan_create(const read_conv_desc &d, TcPlan **out)
 {
     TcGeom g;
-    if (!tc_supported(d) || !tc_geom(d.Cin, d.Cout, d.stride, &g)) {
+    if (!tc_supported(d) || !tc_geom(d.Cin, d.Cout, d.stride, &g, desc_chan_gran(d))) {
         set_error("tcgen05 conv: unsupported layer");
         return READ_ERR_UNSUPPORTED;
     }
@@ -703,22 +755,25 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     const bool s2 = d.stride == 2;
     const int halo_rows = s2 ? TC_TH + 1 : TC_TH + d.k - 1, halo_w = s2 ? TC_TW + 1 : TC_TW + d.k - 1;
     const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    {   // activations: dims {C, W, H, B}; box = one halo tile for one filter column
-        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.B};
-        cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-        // stride 2: traversal stride 2 in x and y; the box spans 2n-1 input elements and delivers n of them
-        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, (cuuint32_t)(s2 ? 2 * halo_w - 1 : halo_w),
-                             (cuuint32_t)(s2 ? 2 * halo_rows - 1 : halo_rows), 1};
-        cuuint32_t estr[4] = {1, s2 ? 2u : 1u, s2 ? 2u : 1u, 1};
-        CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.src[0].ptr), dims, strides, box,
+    for (int si = 0; si < d.n_src; ++si) {   // activations: dims {C, W, H, B}; box = one halo tile (all filter taps)
+        const read_src &sv = d.src[si];
+        const unsigned f = (d.n_src > 1 && sv.mode == READ_SRC_NEAREST_DOWN) ? (unsigned)sv.factor : (s2 ? 2u : 1u);
+        cuuint64_t dims[4] = {(cuuint64_t)sv.C, (cuuint64_t)sv.W, (cuuint64_t)sv.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)sv.C * 2, (cuuint64_t)sv.W * sv.C * 2, (cuuint64_t)sv.H * sv.W * sv.C * 2};
+        // traversal stride f in x and y (conv stride 2, or a nearest-down source): the box spans (n-1)*f+1 input
+        // elements and delivers n of them
+        cuuint32_t box[4] = {(cuuint32_t)g.cin_blk, (cuuint32_t)((halo_w - 1) * f + 1), (cuuint32_t)((halo_rows - 1) * f + 1), 1};
+        cuuint32_t estr[4] = {1, f, f, 1};
+        CUresult r = enc(&p->tmA.a[si], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(sv.ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
-            set_error("tcgen05 conv: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+            set_error("tcgen05 conv: cuTensorMapEncodeTiled(activations, source %d) failed with %d", si, (int)r);
             delete p;
             return READ_ERR_CUDA;
         }
     }
+    for (int si = d.n_src; si < READ_MAX_SRC; ++si) p->tmA.a[si] = p->tmA.a[0];
     {   // weights: dims {cin_blk, taps * kchunks * n_total}
         const cuuint64_t rows = (cuuint64_t)d.k * d.k * g.kchunks * 2 * g.cout_pad;
         cuuint64_t dims[2] = {(cuuint64_t)g.cin_blk, rows};
@@ -742,6 +797,20 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
     a.halo_w = halo_w;
     a.stride = d.stride;
+    a.n_src = d.n_src;
+    {
+        int kc = 0;
+        for (int si = 0; si < READ_MAX_SRC; ++si) {
+            int sh = 0;
+            if (si < d.n_src) {
+                kc += d.src[si].C / g.cin_blk;
+                if (d.n_src > 1 && d.src[si].mode == READ_SRC_NEAREST_DOWN)
+                    while ((1 << sh) < d.src[si].factor) ++sh;
+            }
+            a.src_kc_end[si] = kc;
+            a.src_shift[si] = sh;
+        }
+    }
     a.a_tx_bytes = (uint32_t)halo_rows * halo_w * g.cin_blk * 2u;
     a.tile_bytes = (a.a_tx_bytes + 1023u) & ~1023u;    // tiles stay 1 KB aligned (swizzle patterns are address based)
     a.a_bytes = s2 ? 4u * a.tile_bytes : a.tile_bytes;
@@ -848,6 +917,9 @@ void tc_plan_destroy(TcPlan *p) { delete p; }
 
 using namespace rb;
 
+static int pack_tc_impl(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, int chan_gran, void *out_bf16,
+                        void *stream);
+
 extern "C" {
 
 int64_t read_tc_weight_elems(int Cout, int Cin, int k)
@@ -862,13 +934,27 @@ int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, in
     return read_pack_weights_tc_strided(wf, wm, Cout, Cin, k, 1, out_bf16, stream);
 }
 
+int read_pack_weights_tc_for(const read_conv_desc *d, const float *wf, const float *wm, void *out_bf16, void *stream)
+{
+    RB_CHECK_ARG(d != nullptr, "pack_tc: null descriptor");
+    return pack_tc_impl(wf, wm, d->Cout, d->Cin, d->k, d->stride, desc_chan_gran(*d), out_bf16, stream);
+}
+
 int read_pack_weights_tc_strided(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, void *out_bf16,
                                  void *stream)
+{
+    return pack_tc_impl(wf, wm, Cout, Cin, k, stride, 64, out_bf16, stream);
+}
+
+}  // extern "C"
+
+static int pack_tc_impl(const float *wf, const float *wm, int Cout, int Cin, int k, int stride, int chan_gran, void *out_bf16,
+                        void *stream)
 {
     TcGeom g;
     RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc: null pointer");
     RB_CHECK_ARG(stride == 1 || stride == 2, "pack_tc: stride must be 1 or 2");
-    RB_CHECK_ARG(tc_geom(Cin, Cout, stride, &g), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
+    RB_CHECK_ARG(tc_geom(Cin, Cout, stride, &g, chan_gran), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
     const long long total = (long long)k * k * Cin * 2 * g.cout_pad;
     long long blocks = (total + 255) / 256;
     if (blocks > 65535) blocks = 65535;
@@ -877,5 +963,3 @@ int read_pack_weights_tc_strided(const float *wf, const float *wm, int Cout, int
     RB_LAUNCH_CHECK();
     return READ_OK;
 }
-
-}  // extern "C"

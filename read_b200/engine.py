@@ -112,7 +112,7 @@ class UNetEngine:
         stream = L.stream_ptr()
         if kind == "tma":
             wtc = torch.empty(lib.read_tc_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=self.device)
-            L.check(lib.read_pack_weights_tc_strided(wf.data_ptr(), wm.data_ptr(), cout, cin, k, stride, wtc.data_ptr(), stream))
+            L.check(lib.read_pack_weights_tc_for(ctypes.byref(d), wf.data_ptr(), wm.data_ptr(), wtc.data_ptr(), stream))
             d.w_tc, d.impl = wtc.data_ptr(), L.CONV_TCGEN05
             keep.append(wtc)
         elif kind == "gather":

@@ -1,0 +1,71 @@
+"""Viewer-side renderer: the device-resident replacement for ``READ.gl.nn.OGL`` (READ/gl/nn.py:76-129).
+
+The reference's ``OGL`` draws index maps with OpenGL (``MultiscaleRender``), runs ``model(input_dict, return_input=True)``
+and returns ``{'output': [H,W,4] f32 on the GPU (RGB + alpha 1), 'net_input': ...}`` (nn.py:113-129); ``viewer.py:267``
+then flips the frame vertically for display.  ``FrameRenderer`` keeps that output contract but needs no OpenGL: one
+pass over the point cloud on the GPU (``NetAndTexture.render``) and ONE small kernel that writes the displayable
+``[H,W,4]`` surface (alpha, optional vertical flip) straight from the net's output planes.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from .compose import NetAndTexture
+from .texture import PointTexture
+from .unet import UNet
+
+
+class FrameRenderer:
+    def __init__(self, xyz, net_state_dict, texture, viewport_size, supersampling=1, temporal_average=False,
+                 device=None, flip_vertical=False, n_levels=4):
+        """xyz: [N,3] float32 (numpy / tensor); net_state_dict: UNet checkpoint ``state_dict``; texture: the
+        ``[1,8,N]`` descriptor tensor (``PointTexture.texture_``) or a ``PointTexture``; viewport_size: (W, H)."""
+        W, H = int(viewport_size[0]), int(viewport_size[1])
+        factor = 16
+        assert W % 16 == 0, f'set width {factor * (W // factor)}'          # READ/gl/nn.py:107-109
+        assert H % 16 == 0, f'set height {factor * (H // factor)}'
+        if supersampling != 1 or temporal_average:
+            # the fused path renders at the net's resolution; the index-map path (NetAndTexture.forward) keeps both options
+            raise NotImplementedError("FrameRenderer: supersampling / temporal_average are served by NetAndTexture.forward")
+        L.require_device(None if device is None else torch.device(device).index)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.W, self.H, self.n_levels = W, H, n_levels
+        self.flip_vertical = bool(flip_vertical)
+        xyz = torch.as_tensor(np.asarray(xyz, dtype=np.float32) if not torch.is_tensor(xyz) else xyz, dtype=torch.float32)
+        self.xyz = xyz.contiguous().to(self.device)
+        net = UNet()
+        net.load_state_dict(net_state_dict, strict=True)
+        if not isinstance(texture, PointTexture):
+            t = torch.as_tensor(texture, dtype=torch.float32)
+            assert t.dim() == 3 and t.shape[0] == 1 and t.shape[2] == self.xyz.shape[0], "texture must be [1,D,N]"
+            tex = PointTexture(t.shape[1], t.shape[2])
+            with torch.no_grad():
+                tex.texture_.copy_(t)
+            texture = tex
+        self.model = NetAndTexture(net, {0: texture}, 1)
+        self.model.load_textures(0)
+        self.model.to(self.device).eval()
+        self._rgba = torch.empty((H, W, 4), dtype=torch.float32, device=self.device)
+
+    @classmethod
+    def from_checkpoints(cls, xyz, net_ckpt, texture_ckpt, viewport_size, **kw):
+        """The reference's checkpoint format: ``{'state_dict': ..., 'args': ...}`` (READ/utils/train.py:42-65)."""
+        net_sd = torch.load(net_ckpt, map_location="cpu")["state_dict"]
+        tex_sd = torch.load(texture_ckpt, map_location="cpu")["state_dict"]
+        return cls(xyz, net_sd, tex_sd["texture_"], viewport_size, **kw)
+
+    @staticmethod
+    def total_matrix(proj_matrix, view_matrix):
+        """proj @ inv(view) in float32 on the host, the call src/READ/gl/myrender.py:28-30 makes."""
+        proj = np.asarray(proj_matrix, dtype=np.float32)
+        view = np.asarray(view_matrix, dtype=np.float32)
+        return (proj @ np.linalg.inv(view)).astype(np.float32)
+
+    def infer(self, proj_matrix, view_matrix):
+        """-> {'output': [H,W,4] f32 cuda tensor (RGB, alpha 1; flipped if ``flip_vertical``), 'net_input': None}."""
+        m = torch.from_numpy(self.total_matrix(proj_matrix, view_matrix).reshape(1, 4, 4)).to(self.device)
+        with torch.no_grad():
+            out = self.model.render(self.xyz, m, self.W, self.H, n_levels=self.n_levels)      # [1,3,H,W] f32
+        L.check(L.load().read_frame_to_rgba(out.data_ptr(), self.H, self.W, int(self.flip_vertical), 1.0,
+                                             self._rgba.data_ptr(), L.stream_ptr()))
+        return {'output': self._rgba, 'net_input': None}

@@ -85,7 +85,7 @@ def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=Fa
     stream = L.stream_ptr()
     if impl == L.CONV_TCGEN05:
         wt = torch.empty(lib.read_tc_weight_elems(cout, cin, k), dtype=torch.bfloat16, device=d)
-        L.check(lib.read_pack_weights_tc_strided(dv[0].data_ptr(), dv[1].data_ptr(), cout, cin, k, stride, wt.data_ptr(), stream))
+        L.check(lib.read_pack_weights_tc_for(ctypes.byref(dsc), dv[0].data_ptr(), dv[1].data_ptr(), wt.data_ptr(), stream))
         dsc.w_tc = wt.data_ptr()
         keep.append(wt)
     elif impl == L.CONV_TCGEN05_GATHER:
@@ -188,6 +188,11 @@ TC_CASES = [
     ("4x4 s2 256->128 (feat_extract.7)", [(256, 32, 16, "id", 1)], 128, 4, True, {"stride": 2}),
     ("4x4 s2 64->32 (feat_extract.4)", [(64, 64, 48, "id", 1)], 32, 4, True, {"stride": 2}),
     ("3x3 s2 persistent, 1200 tiles", [(32, 640, 960, "id", 1)], 64, 3, True, {"stride": 2}),
+    # virtual concat on the TMA path (1x1): identity + nearest-down sources, one tensor map per source
+    ("decoder merge 32+32 -> 32 (Convs.2: 32-channel K chunks)", [(32, 40, 56, "id", 1), (32, 40, 56, "id", 1)], 32, 1, True, {}),
+    ("decoder merge 128+128 -> 128 (Convs.0)", [(128, 24, 24, "id", 1), (128, 24, 24, "id", 1)], 128, 1, True, {}),
+    ("concat down4 + down2 + id (AFF2 without its upsampled source)", [(32, 64, 96, "down", 4), (64, 32, 48, "down", 2), (128, 16, 24, "id", 1)], 64, 1, True, {}),
+    ("persistent concat 64+64 -> 64, 1280 tiles", [(64, 256, 640, "id", 1), (64, 256, 640, "id", 1)], 64, 1, False, {"residual": True}),
 ]
 
 

@@ -145,3 +145,28 @@ def test_fused_render_path_equals_index_map_path(synth_sd):
 def test_non_multiple_of_16_is_rejected(synth_sd):
     with pytest.raises(RuntimeError, match="multiples of 16"):
         UNetEngine(synth_sd, 1, 40, 64, dev())
+
+
+def test_frame_renderer_matches_ogl_infer_contract():
+    """read_b200.viewer.FrameRenderer.infer == READ/gl/nn.py:123-124 (permute + alpha) on the fused render, and the
+    vertical flip of viewer.py:267."""
+    import numpy as np
+    from read_b200 import synth
+    from read_b200.viewer import FrameRenderer
+    W, H, n = 128, 64, 40_000
+    xyz = synth.street_scene(n, depth=60.0, seed=5)
+    sd = synth.synth_state_dict(synth.SEED)
+    tex = torch.rand((1, 8, n), generator=torch.Generator().manual_seed(2))
+    proj, view = synth.camera_batch(W, H, [3])
+    r = FrameRenderer(xyz, sd, tex, (W, H))
+    got = r.infer(proj[0], view[0])['output'].clone()
+    m = torch.from_numpy(synth.total_matrix(proj, view)).cuda()
+    with torch.no_grad():
+        ref = r.model.render(r.xyz, m, W, H)[0].permute(1, 2, 0)
+    want = torch.cat([ref, ref[:, :, :1] * 0 + 1], 2).contiguous()
+    assert tuple(got.shape) == (H, W, 4) and got.is_cuda and got.dtype == torch.float32
+    assert torch.equal(got, want)
+    rf = FrameRenderer(xyz, sd, tex, (W, H), flip_vertical=True)
+    assert torch.equal(rf.infer(proj[0], view[0])['output'], want.flip(0))
+    with pytest.raises(AssertionError, match="set width 112"):
+        FrameRenderer(xyz, sd, tex, (120, 64))
