@@ -138,7 +138,10 @@ int read_gather_backward(const float *grad_out, const float *ids, int B, int D, 
  * ---------------------------------------------------------------------------------------- */
 enum { READ_ACT_F32 = 0, READ_ACT_BF16 = 1 };
 enum { READ_SRC_IDENTITY = 0, READ_SRC_NEAREST_DOWN = 1, READ_SRC_NEAREST_UP = 2, READ_SRC_BILINEAR_UP4 = 3 };
-enum { READ_OUT_NHWC = 0, READ_OUT_NCHW_F32 = 1 };
+enum { READ_OUT_NHWC = 0, READ_OUT_NCHW_F32 = 1,
+       /* pre-activation accumulators [conv_f | conv_m] (no bias / activation / BN), NHWC with 2*Cout channels: one term of a
+        * 1x1 conv over a concat whose other sources live at a finer resolution (see `addin`) */
+       READ_OUT_RAW_NHWC = 2 };
 enum { READ_CONV_AUTO = 0, READ_CONV_GENERIC = 1, READ_CONV_TCGEN05 = 2, READ_CONV_TCGEN05_GATHER = 3 };
 
 typedef struct read_src {
@@ -167,6 +170,13 @@ typedef struct read_conv_desc {
     void *out2;                     /* optional second NHWC output: out2 = y * out2_mul (feeds a FAM) */
     const void *out2_mul;
     int32_t impl;                   /* READ_CONV_* : which kernel (must match the packed weights) */
+    /* optional RAW tensor [B, ceil(Hout/2), ceil(Wout/2), 2*Cout] (activation dtype) added, nearest-upsampled x2, to the
+     * accumulators BEFORE bias / activation.  A 1x1 conv commutes with nearest upsampling, so
+     *   conv1x1(cat[a, up2(b)]) == conv1x1_a(a) + up2(conv1x1_b(b)):
+     * the coarse sources of the AFF heads (unet.py:79-89,252-254) are convolved at their own resolution into RAW tensors
+     * and enter here, instead of being gathered 4..64 times each at the fine resolution.  tcgen05 TMA kernel only. */
+    const void *addin;
+    int32_t addin_H, addin_W;
 } read_conv_desc;
 
 typedef struct read_conv_plan read_conv_plan;

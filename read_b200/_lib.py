@@ -19,7 +19,7 @@ FEAT_NCHW_F32, FEAT_NHWC_F32, FEAT_NHWC_BF16 = 0, 1, 2
 TEXACT = {"none": 0, "sigmoid": 1, "tanh": 2}
 ACT_F32, ACT_BF16 = 0, 1
 SRC_IDENTITY, SRC_NEAREST_DOWN, SRC_NEAREST_UP, SRC_BILINEAR_UP4 = 0, 1, 2, 3
-OUT_NHWC, OUT_NCHW_F32 = 0, 1
+OUT_NHWC, OUT_NCHW_F32, OUT_RAW_NHWC = 0, 1, 2
 CONV_AUTO, CONV_GENERIC, CONV_TCGEN05, CONV_TCGEN05_GATHER = 0, 1, 2, 3
 
 
@@ -39,6 +39,7 @@ class ReadConvDesc(ctypes.Structure):
         ("bias_f", c_vp), ("bias_m", c_vp), ("bn_scale", c_vp), ("bn_shift", c_vp),
         ("residual", c_vp), ("out", c_vp), ("out_mode", ctypes.c_int32),
         ("out2", c_vp), ("out2_mul", c_vp), ("impl", ctypes.c_int32),
+        ("addin", c_vp), ("addin_H", ctypes.c_int32), ("addin_W", ctypes.c_int32),
     ]
 
 

@@ -83,6 +83,9 @@ struct TcArgs {
     float *out_nchw;                      // final layer only
     __nv_bfloat16 *out2;
     const __nv_bfloat16 *out2_mul;
+    const __nv_bfloat16 *addin;           // RAW [B, addin_H, addin_W, n_tile] added (nearest x2) to the accumulators, or null
+    int addin_H, addin_W;
+    int raw;                              // RAW output: store the accumulators themselves, [.., n_tile] channels
 };
 
 // tile index -> (n tile, tile x, tile y, image) without integer division: fdiv_small, conv_common.cuh
@@ -177,7 +180,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         }
         for (int i = 0; i < TC_MAX_ACC; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, NTHR == 640 ? (uint32_t)(a.n_tile >> 3) : (NTHR - 128) / 32);   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
+            mbar_init(tempty0 + 8 * i, NTHR == 640 ? (a.raw ? 16u : (uint32_t)(a.n_tile >> 3)) : (NTHR - 128) / 32);   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
         }
         mbar_init(bres, 1);
         mbar_fence_init();
@@ -432,6 +435,39 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                 // from two different warps at different times) and half as many per-tile hand-shakes per output.
                 // EPI fixes the layer kind at compile time (1: ELU, no residual - ResBlock main.0; 2: no activation +
                 // residual - ResBlock main.1; 0: runtime flags).
+                if (EPI == 0 && a.raw) {
+                    // RAW output (one term of a 1x1 conv over a multi-resolution concat): every warp, every tile; 16-column
+                    // chunks sub, sub + 4, .. of the accumulator; optional add-in of the next-coarser RAW tensor
+                    const int opix = ((b * a.H + y) * a.W + x) * a.n_tile;
+                    const int apix = ((b * a.addin_H + (y >> 1)) * a.addin_W + (x >> 1)) * a.n_tile;
+                    mbar_wait(tfull0 + 8 * acc, acc_ph);
+                    tcgen05_fence_after();
+                    for (int c = sub; c < (a.n_tile >> 4); c += 4) {
+                        uint32_t v[16];
+                        tmem_ld16(trow + (uint32_t)(c * 16), v);
+                        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+                        if (a.addin != nullptr && inside) {
+                            a0 = __ldg(reinterpret_cast<const uint4 *>(a.addin + apix + c * 16));
+                            a1 = __ldg(reinterpret_cast<const uint4 *>(a.addin + apix + c * 16) + 1);
+                        }
+                        tmem_ld_wait();
+                        if (inside) {
+                            const uint32_t aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                pk[j] = cvt_bf16x2(__uint_as_float(v[2 * j]) + __uint_as_float(aa[j] << 16),
+                                                   __uint_as_float(v[2 * j + 1]) + __uint_as_float(aa[j] & 0xFFFF0000u));
+                            uint4 *op = reinterpret_cast<uint4 *>(a.out + opix + c * 16);
+                            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    continue;
+                }
                 const bool elu = EPI == 1 ? true : (EPI == 2 ? false : a.elu != 0);
                 const bool has_res = EPI == 2 ? true : (EPI == 1 ? false : a.residual != nullptr);
                 const bool has_out2 = EPI != 0 ? false : a.out2 != nullptr;
@@ -451,6 +487,15 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                 const int co = nt * half + chunk * 16;
                 const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;                  // < 2^31 (checked by the host)
                 uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, ml0 = rs0, ml1 = rs0;
+                uint4 af0 = rs0, af1 = rs0, am0 = rs0, am1 = rs0;            // add-in: f and m columns of this item
+                const bool has_addin = EPI == 0 && a.addin != nullptr;
+                if (has_addin && inside && mem_ok) {
+                    const __nv_bfloat16 *ap = a.addin + ((b * a.addin_H + (y >> 1)) * a.addin_W + (x >> 1)) * a.n_tile + chunk * 16;
+                    af0 = __ldg(reinterpret_cast<const uint4 *>(ap));
+                    af1 = __ldg(reinterpret_cast<const uint4 *>(ap) + 1);
+                    am0 = __ldg(reinterpret_cast<const uint4 *>(ap + half));
+                    am1 = __ldg(reinterpret_cast<const uint4 *>(ap + half) + 1);
+                }
                 if (inside && mem_ok) {
                     if (has_res) {
                         rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
@@ -471,6 +516,17 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (has_addin) {        // pre-activation terms computed at the coarser resolution (nearest x2)
+                    const uint32_t fa[8] = {af0.x, af0.y, af0.z, af0.w, af1.x, af1.y, af1.z, af1.w};
+                    const uint32_t ma[8] = {am0.x, am0.y, am0.z, am0.w, am1.x, am1.y, am1.z, am1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f16[2 * j] = __float_as_uint(__uint_as_float(f16[2 * j]) + __uint_as_float(fa[j] << 16));
+                        f16[2 * j + 1] = __float_as_uint(__uint_as_float(f16[2 * j + 1]) + __uint_as_float(fa[j] & 0xFFFF0000u));
+                        m16[2 * j] = __float_as_uint(__uint_as_float(m16[2 * j]) + __uint_as_float(ma[j] << 16));
+                        m16[2 * j + 1] = __float_as_uint(__uint_as_float(m16[2 * j + 1]) + __uint_as_float(ma[j] & 0xFFFF0000u));
+                    }
+                }
                 float yv[16];
                 if (elu) {              // warp-uniform: the no-activation layers skip the ex2 path entirely
 #pragma unroll
@@ -699,8 +755,15 @@ bool tc_supported(const read_conv_desc &d)
     }
     if (d.Cout <= 8) {
         if (d.out_mode != READ_OUT_NCHW_F32 || d.residual || d.out2) return false;   // final layer only
-    } else if (d.out_mode != READ_OUT_NHWC) {
+    } else if (d.out_mode != READ_OUT_NHWC && d.out_mode != READ_OUT_RAW_NHWC) {
         return false;
+    }
+    if (d.out_mode == READ_OUT_RAW_NHWC || d.addin != nullptr) {
+        // terms of a 1x1 conv over a multi-resolution concat: served by the lean epilogue (Cout 16 / 32 / 64)
+        if (d.k != 1 || d.stride != 1) return false;
+        if (!(d.Cout == 16 || d.Cout == 32 || d.Cout == 64)) return false;
+        if (d.out_mode == READ_OUT_RAW_NHWC && (d.residual || d.out2)) return false;
+        if ((long long)d.B * d.Hout * d.Wout * 2 * d.Cout >= (1ll << 31)) return false;
     }
     TcGeom g;
     if (!tc_geom(d.Cin, d.Cout, d.stride, &g, desc_chan_gran(d))) return false;
@@ -749,6 +812,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.w_tc) & 127) == 0, "tcgen05 conv: packed weights must be 128B aligned");
     RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "tcgen05 conv: output must be 16B aligned");
     RB_CHECK_ARG(d.residual == nullptr || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, "tcgen05 conv: residual must be 16B aligned");
+    RB_CHECK_ARG(d.addin == nullptr || (reinterpret_cast<uintptr_t>(d.addin) & 15) == 0, "tcgen05 conv: addin must be 16B aligned");
     TcPlan *p = new (std::nothrow) TcPlan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
 
@@ -847,6 +911,9 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.out_nchw = static_cast<float *>(d.out);
     a.out2 = static_cast<__nv_bfloat16 *>(d.out2);
     a.out2_mul = static_cast<const __nv_bfloat16 *>(d.out2_mul);
+    a.addin = static_cast<const __nv_bfloat16 *>(d.addin);
+    a.addin_H = d.addin_H; a.addin_W = d.addin_W;
+    a.raw = d.out_mode == READ_OUT_RAW_NHWC ? 1 : 0;
     p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + 8 * BAR_PARAMS + 16 * (size_t)g.cout_pad + 64;
     *out = p;
     return READ_OK;

@@ -592,6 +592,7 @@ static bool g_geom(int Cin, int Cout, int k, GGeom *g)
 bool tcg_supported(const read_conv_desc &d)
 {
     if (d.act_dtype != READ_ACT_BF16 || d.mul != nullptr) return false;
+    if (d.out_mode == READ_OUT_RAW_NHWC || d.addin != nullptr) return false;      // TMA kernel only
     if (d.out_mode == READ_OUT_NHWC && d.Cout % 8 != 0) return false;
     for (int i = 0; i < d.n_src; ++i) {
         if (d.src[i].C % 8 != 0) return false;

@@ -15,7 +15,7 @@ _MODE = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_U
 
 
 class _Layer:
-    __slots__ = ("name", "plan", "impl", "keep", "flops")
+    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride")
 
 
 class UNetEngine:
@@ -60,8 +60,13 @@ class UNetEngine:
         return wf, wm, bf, bm, scale, shift
 
     # ------------------------------------------------------------------ one fused gated conv
-    def _conv(self, prefix, srcs, cout, k, stride, elu, residual=None, out2_mul=None, final=False):
-        """srcs: list of (tensor [B,h,w,c], mode, factor).  Returns out (and out2 if out2_mul)."""
+    def _conv(self, prefix, srcs, cout, k, stride, elu, residual=None, out2_mul=None, final=False,
+              raw=False, addin=None, cin_slice=None, name=None):
+        """srcs: list of (tensor [B,h,w,c], mode, factor).  Returns out (and out2 if out2_mul).
+        ``raw``: store the pre-activation accumulators [f | m] (2*cout channels) instead of the gated output;
+        ``addin``: RAW tensor of the next-coarser resolution added (nearest x2) before the activation;
+        ``cin_slice`` = (c0, c1): this launch covers input channels [c0, c1) of the layer's weights (one term of a 1x1 conv
+        over a multi-resolution concat, see ``_aff``)."""
         lib = self.lib
         d = L.ReadConvDesc()
         d.act_dtype = self.act_code
@@ -81,7 +86,14 @@ class UNetEngine:
         pad = int((k - 1) / 2)                                   # unet.py:29
         hout = (hin + 2 * pad - k) // stride + 1
         wout = (win + 2 * pad - k) // stride + 1
-        wf, wm, bf, bm, scale, shift = self._params(prefix, cin, cout, k)
+        if cin_slice is None:
+            wf, wm, bf, bm, scale, shift = self._params(prefix, cin, cout, k)
+        else:
+            c0, c1 = cin_slice
+            assert c1 - c0 == cin, (prefix, cin_slice, cin)
+            sdw = self.sd[prefix + ".block.conv_f.weight"]
+            wf, wm, bf, bm, scale, shift = self._params(prefix, sdw.shape[1], cout, k)
+            wf, wm = wf[:, c0:c1].contiguous(), wm[:, c0:c1].contiguous()
         d.B, d.Hin, d.Win, d.Cin = self.B, hin, win, cin
         d.Hout, d.Wout, d.Cout = hout, wout, cout
         d.k, d.stride, d.pad, d.elu = k, stride, pad, int(elu)
@@ -89,6 +101,9 @@ class UNetEngine:
         if final:
             out = torch.empty((self.B, cout, hout, wout), dtype=torch.float32, device=self.device)
             d.out_mode = L.OUT_NCHW_F32
+        elif raw:
+            out = torch.empty((self.B, hout, wout, 2 * cout), dtype=self.adt, device=self.device)
+            d.out_mode = L.OUT_RAW_NHWC
         else:
             out = torch.empty((self.B, hout, wout, cout), dtype=self.adt, device=self.device)
             d.out_mode = L.OUT_NHWC
@@ -101,10 +116,17 @@ class UNetEngine:
             assert tuple(out2_mul.shape) == (self.B, hout, wout, cout)
             out2 = torch.empty_like(out)
             d.out2, d.out2_mul = out2.data_ptr(), out2_mul.data_ptr()
-        keep = [wf, wm, bf, bm, scale, shift, out, out2, residual, out2_mul] + [s[0] for s in srcs]
+        if addin is not None:
+            assert tuple(addin.shape) == (self.B, (hout + 1) // 2, (wout + 1) // 2, 2 * cout), (prefix, tuple(addin.shape))
+            d.addin, d.addin_H, d.addin_W = addin.data_ptr(), addin.shape[1], addin.shape[2]
+        keep = [wf, wm, bf, bm, scale, shift, out, out2, residual, out2_mul, addin] + [s[0] for s in srcs]
 
         kind = "generic"
-        if self.bf16 and self.conv_impl != "generic":
+        if raw or addin is not None:
+            d.impl = L.CONV_TCGEN05          # validation: these only exist on the tcgen05 TMA kernel
+            assert self.bf16 and lib.read_conv_tc_supported(ctypes.byref(d)), prefix
+            kind = "tma"
+        elif self.bf16 and self.conv_impl != "generic":
             if lib.read_conv_tc_supported(ctypes.byref(d)):
                 kind = "tma"
             elif self.conv_impl == "auto" and lib.read_conv_tcg_supported(ctypes.byref(d)):
@@ -130,8 +152,9 @@ class UNetEngine:
         plan = L.c_vp()
         L.check(lib.read_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
         ly = _Layer()
-        ly.name, ly.plan, ly.impl, ly.keep = prefix, plan, lib.read_conv_plan_impl(plan), keep
+        ly.name, ly.plan, ly.impl, ly.keep = (name or prefix), plan, lib.read_conv_plan_impl(plan), keep
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
+        ly.k, ly.stride = k, stride
         self.layers.append(ly)
         self.ops.append(ly)
         return (out, out2) if out2_mul is not None else out
@@ -145,7 +168,7 @@ class UNetEngine:
         B, h, w, c = t.shape
         out = torch.empty((B, 4 * h, 4 * w, c), dtype=self.adt, device=self.device)
         op = _Layer()
-        op.name, op.plan, op.impl, op.flops = f"upsample4({h}x{w}x{c})", None, -1, 0
+        op.name, op.plan, op.impl, op.flops, op.k, op.stride = f"upsample4({h}x{w}x{c})", None, -1, 0, 0, 0
         op.keep = [t, out, (t.data_ptr(), B, h, w, c, out.data_ptr())]
         self.ops.append(op)
         return (out, "id", 1)
@@ -173,7 +196,31 @@ class UNetEngine:
         return self._conv(f"{fam}.merge", [(zz, "id", 1)], c, 3, 1, False, residual=z)
 
     def _aff(self, idx, srcs, c):
-        a = self._conv(f"AFFs.{idx}.conv.0", srcs, c, 1, 1, True)
+        """AFF head (unet.py:79-89): BC1x1_elu(cat of the four scales) then BC3x3.  On the tensor-core path the 1x1 conv over
+        the concat is split by linearity: a 1x1 conv commutes with nearest upsampling, so every source COARSER than the
+        output is convolved at its own resolution into a RAW [f|m] tensor that is added (nearest x2, coarse to fine) to the
+        next finer term; the sources at or above the output resolution are TMA sources (identity / traversal-stride) of
+        the final launch.  The reference order cat[res1, res2, res3, z] fixes the weight column ranges."""
+        prefix = f"AFFs.{idx}.conv.0"
+        # measured at C3: the split pays for the full-resolution head (0.35 -> 0.25 ms); at half resolution it is a wash
+        chain_ok = self.bf16 and self.conv_impl == "auto" and c == self.base
+        if chain_ok:
+            coarse = [(i, t, f) for i, (t, mode, f) in enumerate(srcs) if mode == "up"]
+            fine = [(i, sv) for i, sv in enumerate(srcs) if sv[1] != "up"]
+            offs = [0]
+            for t, _, _ in srcs:
+                offs.append(offs[-1] + t.shape[3])
+            chain_ok = len(coarse) >= 1 and all(cf == 2 ** (k + 1) for k, (_, _, cf) in enumerate(coarse)) \
+                and all(t.shape[3] % 32 == 0 for t, _, _ in srcs)
+        if not chain_ok:
+            a = self._conv(prefix, srcs, c, 1, 1, True)
+            return self._conv(f"AFFs.{idx}.conv.1", [(a, "id", 1)], c, 3, 1, False)
+        partial = None
+        for i, t, f in reversed(coarse):                     # coarsest first
+            partial = self._conv(prefix, [(t, "id", 1)], c, 1, 1, False, raw=True, addin=partial,
+                                 cin_slice=(offs[i], offs[i + 1]), name=f"{prefix}[raw 1/{f} term]")
+        i0, i1 = fine[0][0], fine[-1][0]
+        a = self._conv(prefix, [sv for _, sv in fine], c, 1, 1, True, addin=partial, cin_slice=(offs[i0], offs[i1 + 1]))
         return self._conv(f"AFFs.{idx}.conv.1", [(a, "id", 1)], c, 3, 1, False)
 
     def _build(self):

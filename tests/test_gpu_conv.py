@@ -274,3 +274,89 @@ def test_upsample_bilinear4_matches_torch(bf16):
     torch.cuda.synchronize()
     err = float((out.float().permute(0, 3, 1, 2).cpu() - want).abs().max())
     assert err < (2 ** -8 if bf16 else 1e-6), err
+
+
+# ---------------------------------------------------------------- RAW terms + add-in (the AFF heads split by linearity)
+def _pack_tc(lib, dsc, wf, wm, d):
+    wt = torch.empty(lib.read_tc_weight_elems(dsc.Cout, dsc.Cin, dsc.k), dtype=torch.bfloat16, device=d)
+    L.check(lib.read_pack_weights_tc_for(ctypes.byref(dsc), wf.data_ptr(), wm.data_ptr(), wt.data_ptr(), L.stream_ptr()))
+    return wt
+
+
+def _run_1x1(srcs_nchw, modes, cout, elu, raw, addin_nchw, seed):
+    """1x1 gated conv on the tcgen05 TMA kernel with RAW output and/or an add-in; returns (got NCHW, want NCHW)."""
+    lib, d = L.load(), dev()
+    g = torch.Generator().manual_seed(seed)
+    xs = [x.to(torch.bfloat16).float() for x in srcs_nchw]
+    logical = torch.cat([resample(x, m, f) for x, (m, f) in zip(xs, modes)], 1)
+    B, cin, h, w = logical.shape
+    bound = 1.0 / cin ** 0.5
+    wf = ((torch.rand((cout, cin, 1, 1), generator=g) * 2 - 1) * bound).to(torch.bfloat16).float()
+    wm = ((torch.rand((cout, cin, 1, 1), generator=g) * 2 - 1) * bound).to(torch.bfloat16).float()
+    bf, bm = (torch.rand(cout, generator=g) * 2 - 1) * bound, (torch.rand(cout, generator=g) * 2 - 1) * bound
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    f = F.conv2d(logical, wf)
+    m = F.conv2d(logical, wm)
+    if addin_nchw is not None:
+        up = F.interpolate(addin_nchw.to(torch.bfloat16).float(), scale_factor=2)[:, :, :h, :w]
+        f, m = f + up[:, :cout], m + up[:, cout:]
+    if raw:
+        want = torch.cat([f, m], 1)
+    else:
+        f, m = f + bf[None, :, None, None], m + bm[None, :, None, None]
+        want = (F.elu(f) if elu else f) * torch.sigmoid(m) * scale[None, :, None, None] + shift[None, :, None, None]
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(d, torch.bfloat16)
+    dsc = L.ReadConvDesc()
+    dsc.act_dtype, dsc.n_src = L.ACT_BF16, len(xs)
+    keep = []
+    mm = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN}
+    for i, (x, (mo, fa)) in enumerate(zip(xs, modes)):
+        t = nhwc(x); keep.append(t)
+        dsc.src[i].ptr, dsc.src[i].C, dsc.src[i].H, dsc.src[i].W = t.data_ptr(), x.shape[1], x.shape[2], x.shape[3]
+        dsc.src[i].mode, dsc.src[i].factor = mm[mo], fa
+    dsc.B, dsc.Hin, dsc.Win, dsc.Cin, dsc.Hout, dsc.Wout, dsc.Cout = B, h, w, cin, h, w, cout
+    dsc.k, dsc.stride, dsc.pad, dsc.elu = 1, 1, 0, int(elu)
+    dv = [t.to(d).contiguous() for t in (wf, wm, bf, bm, scale, shift)]
+    dsc.bias_f, dsc.bias_m, dsc.bn_scale, dsc.bn_shift = (t.data_ptr() for t in dv[2:])
+    dsc.impl = L.CONV_TCGEN05
+    oc = 2 * cout if raw else cout
+    out = torch.full((B, h, w, oc), float("nan"), dtype=torch.bfloat16, device=d)
+    dsc.out, dsc.out_mode = out.data_ptr(), (L.OUT_RAW_NHWC if raw else L.OUT_NHWC)
+    if addin_nchw is not None:
+        ad = nhwc(addin_nchw); keep.append(ad)
+        dsc.addin, dsc.addin_H, dsc.addin_W = ad.data_ptr(), ad.shape[1], ad.shape[2]
+    assert lib.read_conv_tc_supported(ctypes.byref(dsc)) == 1
+    wt = _pack_tc(lib, dsc, dv[0], dv[1], d)
+    dsc.w_tc = wt.data_ptr()
+    plan = L.c_vp()
+    L.check(lib.read_conv_plan_create(ctypes.byref(dsc), ctypes.byref(plan)))
+    L.check(lib.read_conv_plan_launch(plan, L.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.read_conv_plan_destroy(plan)
+    return out.float().permute(0, 3, 1, 2).cpu(), want
+
+
+@pytest.mark.parametrize("cout,cin,h,w,with_addin", [(32, 256, 17, 30, False), (32, 128, 34, 60, True), (64, 128, 33, 23, True),
+                                                      (32, 64, 256, 320, True)])
+def test_tcgen05_raw_term_matches_torch(cout, cin, h, w, with_addin):
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((2, cin, h, w), generator=g) * 2 - 1
+    addin = (torch.rand((2, 2 * cout, (h + 1) // 2, (w + 1) // 2), generator=g) * 2 - 1) if with_addin else None
+    got, want = _run_1x1([x], [("id", 1)], cout, False, True, addin, seed=1)
+    assert torch.isfinite(got).all(), "outputs left unwritten"
+    tol = 2 ** -8 * float(want.abs().max()) + 1e-3           # fp32 accumulate + add, one bf16 rounding
+    assert float((got - want).abs().max()) < tol
+
+
+@pytest.mark.parametrize("cout", [32, 64])
+def test_tcgen05_addin_gated_matches_torch(cout):
+    """Final term of an AFF head: two TMA sources (one nearest-down) + the coarse terms as add-in, then the gate."""
+    g = torch.Generator().manual_seed(4)
+    h, w = 40, 56
+    a = torch.rand((2, 32, 2 * h, 2 * w), generator=g) * 2 - 1        # read with traversal stride 2
+    b = torch.rand((2, 64, h, w), generator=g) * 2 - 1
+    addin = torch.rand((2, 2 * cout, h // 2, w // 2), generator=g) * 2 - 1
+    got, want = _run_1x1([a, b], [("down", 2), ("id", 1)], cout, True, False, addin, seed=2)
+    assert torch.isfinite(got).all(), "outputs left unwritten"
+    tol = 2 ** -8 * float(want.abs().max()) + 4e-3
+    assert float((got - want).abs().max()) < tol
