@@ -78,6 +78,13 @@ int read_raster_project(const float *xyz, int64_t n, int64_t id_base, const floa
 int read_raster_project_direct(const float *xyz, int64_t n, int64_t id_base, const float *total_m, int B,
                                int W, int H, int L, uint64_t *zbuf, void *stream);
 int read_raster_derive_levels(int B, int W, int H, int L, uint64_t *zbuf, void *stream);
+/* Single-view frame path over a spatially sorted point store: pts4 is [n,4] f32 = (x, y, z, bit pattern of the ORIGINAL
+ * point id), ordered so that neighbouring points are neighbours in space (read_b200.ops.SortedPoints sorts by the Morton
+ * code of the 3-D grid cell when the scene is loaded, the equivalent of MyRender.update_ds).  Rasterises level 0 only
+ * (nested levels; finish with read_raster_derive_levels or read_pyramid_resolve_gather).  The z-buffer is a min over
+ * (depth | original id) keys, hence identical to read_raster_project_direct on the unsorted cloud. */
+int read_raster_project_sorted(const float *pts4, int64_t n, const float *total_m, int W, int H, int L, uint64_t *zbuf,
+                               void *stream);
 /* Bitmask of levels rasterised with direct atomics (bit l set) for this geometry. */
 unsigned read_raster_direct_mask(int W, int H, int L);
 

@@ -55,6 +55,7 @@ _SIGS = {
     "read_raster_project": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_direct": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_derive_levels": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_raster_project_sorted": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_direct_mask": (c_u32, [c_int, c_int, c_int]),
     "read_zbuf_resolve": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "read_pcpr_forward": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

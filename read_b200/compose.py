@@ -103,7 +103,12 @@ class NetAndTexture(nn.Module):
     # ------------------------------------------------------------------ fused fast path
     @torch.no_grad()
     def render(self, xyz, total_m, W, H, texture_id=0, n_levels=4, want_maps=False):
-        """points [N,3] + total_m [B,4,4] (cuda f32) -> RGB [B,3,H,W] f32, all on device, one pass over the cloud."""
+        """points [N,3] (cuda f32) or an ``ops.SortedPoints`` store + total_m [B,4,4] (cuda f32) -> RGB [B,3,H,W] f32, all on
+        device, one pass over the cloud.  A sorted store serves single-view frames with nested levels; the result is
+        bit-identical to rendering the unsorted cloud (the z-buffer is a min over (depth | original id) keys)."""
+        store = xyz if isinstance(xyz, ops.SortedPoints) else None
+        if store is not None:
+            xyz = store.pts4
         L.require_device()
         texture = self._modules[str(texture_id)]
         B = total_m.shape[0]
@@ -118,13 +123,24 @@ class NetAndTexture(nn.Module):
             # feature maps and leaves level 0 cleared for the next frame
             if not getattr(pyr, "level0_clean", False):
                 pyr.clear()
-            ops.raster_project(pyr, xyz, total_m, derive=False)
+            if store is not None:
+                if B != 1 or pyr.direct_mask != 1:
+                    raise RuntimeError("a SortedPoints store renders one view with nested levels; pass the [N,3] cloud otherwise")
+                ops.raster_project_sorted(pyr, store, total_m)
+            else:
+                ops.raster_project(pyr, xyz, total_m, derive=False)
             ops.pyramid_resolve_gather(tex, pyr, eng.inputs, layout, reset_level0=True)
             pyr.level0_clean = True
         else:
             pyr.clear()
             pyr.level0_clean = False
-            ops.raster_project(pyr, xyz, total_m)
+            if store is not None:
+                if B != 1 or pyr.direct_mask != 1:
+                    raise RuntimeError("a SortedPoints store renders one view with nested levels; pass the [N,3] cloud otherwise")
+                ops.raster_project_sorted(pyr, store, total_m)
+                ops.raster_derive(pyr)
+            else:
+                ops.raster_project(pyr, xyz, total_m)
             for l in range(4):
                 ops.gather_from_zbuf(tex, pyr, l, layout, texture.activation, out=eng.inputs[l])
         out = eng.run()

@@ -58,6 +58,59 @@ def raster_project(pyr, xyz, total_m, id_base=0, derive=True):
                pyr.buf.data_ptr(), L.stream_ptr()))
 
 
+class SortedPoints:
+    """Spatially sorted, device-resident point store for the single-view frame path (the counterpart of
+    ``MyRender.update_ds`` uploading ``scene_data['pointcloud']['xyz']``, src/READ/gl/myrender.py:17-21).
+
+    ``pts4`` is ``[N,4]`` f32 = (x, y, z, bit pattern of the ORIGINAL point id); rows are ordered by the Morton code of the
+    point's 3-D grid cell (``cell`` metres, ties in original order), so consecutive rows are neighbours in space.  The
+    original ids travel with the points: index maps, checkpoints and ``PointTexture`` keep the reference's numbering.
+    Built once per scene with torch ops on the device (scene load, not the per-frame path)."""
+
+    def __init__(self, xyz, cell=0.25):
+        L.require_device()
+        _f32c(xyz, "in_points")
+        if xyz.dim() != 2 or xyz.shape[1] != 3:
+            raise RuntimeError("in_points must be [N,3]")
+        n = xyz.shape[0]
+        if n >= 1 << 32:
+            raise RuntimeError("point ids must fit 32 bits")
+        self.n, self.cell = n, float(cell)
+        if n == 0:
+            self.pts4 = torch.empty((0, 4), dtype=torch.float32, device=xyz.device)
+            self.perm = torch.empty((0,), dtype=torch.int64, device=xyz.device)
+            return
+        lo = xyz.min(0).values
+        q = torch.floor((xyz - lo) / self.cell).to(torch.int64).clamp_(0, (1 << 21) - 1)
+
+        def part1by2(v):                      # spread the low 21 bits: bit i -> bit 3i
+            v = v & 0x1FFFFF
+            v = (v | (v << 32)) & 0x1F00000000FFFF
+            v = (v | (v << 16)) & 0x1F0000FF0000FF
+            v = (v | (v << 8)) & 0x100F00F00F00F00F
+            v = (v | (v << 4)) & 0x10C30C30C30C30C3
+            v = (v | (v << 2)) & 0x1249249249249249
+            return v
+
+        code = part1by2(q[:, 0]) | (part1by2(q[:, 1]) << 1) | (part1by2(q[:, 2]) << 2)
+        self.perm = torch.argsort(code, stable=True)
+        ids = self.perm.to(torch.int32)       # ids < 2^32: keep the low 32 bits (two's complement for ids >= 2^31)
+        pts4 = torch.empty((n, 4), dtype=torch.float32, device=xyz.device)
+        pts4[:, :3] = xyz[self.perm]
+        pts4[:, 3] = ids.view(torch.float32)
+        self.pts4 = pts4
+
+
+def raster_project_sorted(pyr, store, total_m):
+    """Level 0 of a cleared single-view pyramid from a SortedPoints store (finish with raster_derive / pyramid_resolve_gather)."""
+    L.require_device()
+    _f32c(total_m, "total_m")
+    if pyr.B != 1 or total_m.dim() != 3 or total_m.shape[0] != 1:
+        raise RuntimeError("batch_size check")
+    L.check(L.load().read_raster_project_sorted(store.pts4.data_ptr(), store.n, total_m.data_ptr(), pyr.W, pyr.H, pyr.L,
+                                                pyr.buf.data_ptr(), L.stream_ptr()))
+
+
 def raster_derive(pyr):
     L.check(L.load().read_raster_derive_levels(pyr.B, pyr.W, pyr.H, pyr.L, pyr.buf.data_ptr(), L.stream_ptr()))
 

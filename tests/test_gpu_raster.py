@@ -215,3 +215,66 @@ def test_full_size_properties_10m_points():
     assert torch.equal(pyr.buf, full)
     cov = float((gd[0] != 0).mean())
     assert 0.3 < cov <= 1.0, cov
+
+
+@pytest.mark.parametrize("dedup", [1, 0])
+@pytest.mark.parametrize("n,W,H,L,t,depth,cell", [(100_000, 256, 256, 4, 0, 40.0, 0.25), (300_000, 128, 64, 3, 4, 40.0, 0.5),
+                                                    (4097, 64, 32, 2, 9, 60.0, 1.0), (1_000_000, 512, 512, 4, 3, 250.0, 0.25)])
+def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell):
+    """The spatially sorted store (points permuted, original ids carried) with / without the in-warp per-pixel reduction
+    produces the oracle's index and depth maps bit for bit: the z-buffer is order independent."""
+    from read_b200 import _lib as Lb
+    lib = Lb.load()
+    xyz, M = scene_and_cams(n, W, H, [t], depth=depth)
+    d = dev()
+    store = ops.SortedPoints(torch.from_numpy(xyz).to(d), cell=cell)
+    assert torch.equal(torch.sort(store.perm).values, torch.arange(n, device=d))           # a permutation
+    assert torch.equal(store.pts4[:, :3], torch.from_numpy(xyz).to(d)[store.perm])
+    try:
+        Lb.check(lib.read_set_option(b"raster_dedup", dedup))
+        pyr = ops.Pyramid(1, W, H, L, d)
+        pyr.clear()
+        ops.raster_project_sorted(pyr, store, torch.from_numpy(M).to(d))
+        ops.raster_derive(pyr)
+    finally:
+        Lb.check(lib.read_set_option(b"raster_dedup", 0))
+    for l, (w, h) in enumerate(oracle_mod.level_sizes(W, H, L)):
+        gi, gd = ops.zbuf_resolve(pyr, l)
+        oi, od = oracle_mod.pcpr_forward(xyz, M, w, h)
+        np.testing.assert_array_equal(gi.cpu().numpy(), oi, err_msg=f"index level {l}")
+        np.testing.assert_array_equal(gd.cpu().numpy().view(np.uint32), od.view(np.uint32), err_msg=f"depth level {l}")
+
+
+def test_sorted_store_depth_ties_take_the_lowest_original_id(oracle_mod):
+    """Many points with IDENTICAL coordinates (same pixel, same depth bits): lowest original id must win although the sorted
+    store places them in one warp (the in-warp reduction resolves ties with a second atomic on the id)."""
+    rng = np.random.default_rng(1)
+    base = rng.uniform(-0.8, 0.8, size=(200, 3)).astype(np.float32)
+    base[:, 2] = rng.uniform(-0.9, 0.9, size=200).astype(np.float32)
+    xyz = np.repeat(base, 40, axis=0)                      # 40 copies of each point
+    xyz = xyz[rng.permutation(len(xyz))]
+    d = dev()
+    store = ops.SortedPoints(torch.from_numpy(xyz).to(d), cell=0.05)
+    pyr = ops.Pyramid(1, 64, 64, 1, d)
+    pyr.clear()
+    ops.raster_project_sorted(pyr, store, torch.from_numpy(ID).to(d))
+    gi, gd = ops.zbuf_resolve(pyr, 0)
+    oi, od = oracle_mod.pcpr_forward(xyz, ID, 64, 64)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_sorted_store_full_size_equals_unsorted_render():
+    n, W, H, L = 10_000_000, 1920, 1088, 4
+    xyz = synth.street_scene(n)
+    proj, view = synth.camera_batch(W, H, [7])
+    d = dev()
+    m = torch.from_numpy(synth.total_matrix(proj, view)).to(d)
+    x = torch.from_numpy(xyz).to(d)
+    a, b = ops.Pyramid(1, W, H, L, d), ops.Pyramid(1, W, H, L, d)
+    a.clear(); b.clear()
+    ops.raster_project(a, x, m)
+    store = ops.SortedPoints(x)
+    ops.raster_project_sorted(b, store, m)
+    ops.raster_derive(b)
+    assert torch.equal(a.buf, b.buf)
