@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import ops
 from .compose import NetAndTexture
 from .texture import PointTexture
 from .unet import UNet
@@ -33,6 +34,8 @@ class FrameRenderer:
         self.flip_vertical = bool(flip_vertical)
         xyz = torch.as_tensor(np.asarray(xyz, dtype=np.float32) if not torch.is_tensor(xyz) else xyz, dtype=torch.float32)
         self.xyz = xyz.contiguous().to(self.device)
+        # scene load: spatially sorted device store (original ids travel with the points), see ops.SortedPoints
+        self.store = ops.SortedPoints(self.xyz) if ops.level_sizes(W, H, n_levels) == [(W >> l, H >> l) for l in range(n_levels)] else None
         net = UNet()
         net.load_state_dict(net_state_dict, strict=True)
         if not isinstance(texture, PointTexture):
@@ -65,7 +68,8 @@ class FrameRenderer:
         """-> {'output': [H,W,4] f32 cuda tensor (RGB, alpha 1; flipped if ``flip_vertical``), 'net_input': None}."""
         m = torch.from_numpy(self.total_matrix(proj_matrix, view_matrix).reshape(1, 4, 4)).to(self.device)
         with torch.no_grad():
-            out = self.model.render(self.xyz, m, self.W, self.H, n_levels=self.n_levels)      # [1,3,H,W] f32
+            out = self.model.render(self.store if self.store is not None else self.xyz, m, self.W, self.H,
+                                    n_levels=self.n_levels)                                   # [1,3,H,W] f32
         L.check(L.load().read_frame_to_rgba(out.data_ptr(), self.H, self.W, int(self.flip_vertical), 1.0,
                                              self._rgba.data_ptr(), L.stream_ptr()))
         return {'output': self._rgba, 'net_input': None}
