@@ -74,9 +74,9 @@ x0 = torch.from_numpy(synth.street_scene(N)).to(dev)
 for m in mats:
     pyr.clear(); ops.raster_project(pyr, x0, m); torch.cuda.synchronize(); refs0.append(pyr.buf.clone())
 setopt(raster_mode=2)
-for dedup, occ, run in ((0, 0, 0), (0, 0, 1), (0, 0, 4), (0, 0, 16), (1, 0, 0)):
+for dedup, occ, run, nbr in ((0, 0, 0, 0), (0, 0, 0, 1), (0, 0, 16, 1), (0, 0, 32, 1), (0, 4, 0, 1), (1, 0, 0, 0)):
     if True:
-        setopt(raster_dedup=dedup, raster_occupancy=occ, raster_run=run)
+        setopt(raster_dedup=dedup, raster_occupancy=occ, raster_run=run, raster_nbr_filter=nbr)
         bad = 0
         for m, r in zip(mats, refs0):
             pyr.clear(); ops.raster_project_sorted(pyr, store, m); torch.cuda.synchronize()
@@ -88,10 +88,10 @@ for dedup, occ, run in ((0, 0, 0), (0, 0, 1), (0, 0, 4), (0, 0, 16), (1, 0, 0)):
             a.record(); ops.raster_project_sorted(pyr, store, mats[0]); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e3)
         ts = sorted(ts[2:]); med = ts[len(ts) // 2]
-        rows.append({"mode": "sorted", "dedup": dedup, "occ": occ, "run": run, "us_median": med, "us_best": ts[0],
+        rows.append({"mode": "sorted", "dedup": dedup, "occ": occ, "run": run, "nbr_filter": nbr, "us_median": med, "us_best": ts[0],
                      "xyz_GBps": 12 * N / (med * 1e-6) / 1e9, "mismatches": bad})
-        print(f"sorted store dedup {dedup} occ {occ} run {run}: median {med:7.1f} us  best {ts[0]:7.1f} us  "
+        print(f"sorted store dedup {dedup} occ {occ} run {run} nbr {nbr}: median {med:7.1f} us  best {ts[0]:7.1f} us  "
               f"{12 * N / (med * 1e-6) / 1e9:7.1f} GB/s of xyz  mismatching keys vs unsorted render {bad}")
-setopt(raster_dedup=0, raster_occupancy=0, raster_run=0)
+setopt(raster_dedup=0, raster_occupancy=0, raster_run=0, raster_nbr_filter=0)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/raster_modes.json", "w"), indent=1)

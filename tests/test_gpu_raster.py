@@ -217,7 +217,7 @@ def test_full_size_properties_10m_points():
     assert 0.3 < cov <= 1.0, cov
 
 
-@pytest.mark.parametrize("dedup", [1, 0])
+@pytest.mark.parametrize("dedup", [1, 0, 2])          # 1 = in-warp per-pixel reduction, 2 = neighbour filter, 0 = neither (default)
 @pytest.mark.parametrize("n,W,H,L,t,depth,cell", [(100_000, 256, 256, 4, 0, 40.0, 0.25), (300_000, 128, 64, 3, 4, 40.0, 0.5),
                                                     (4097, 64, 32, 2, 9, 60.0, 1.0), (1_000_000, 512, 512, 4, 3, 250.0, 0.25)])
 def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell):
@@ -231,13 +231,15 @@ def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell
     assert torch.equal(torch.sort(store.perm).values, torch.arange(n, device=d))           # a permutation
     assert torch.equal(store.pts4[:, :3], torch.from_numpy(xyz).to(d)[store.perm])
     try:
-        Lb.check(lib.read_set_option(b"raster_dedup", dedup))
+        Lb.check(lib.read_set_option(b"raster_dedup", 1 if dedup == 1 else 0))
+        Lb.check(lib.read_set_option(b"raster_nbr_filter", 1 if dedup == 2 else 0))
         pyr = ops.Pyramid(1, W, H, L, d)
         pyr.clear()
         ops.raster_project_sorted(pyr, store, torch.from_numpy(M).to(d))
         ops.raster_derive(pyr)
     finally:
         Lb.check(lib.read_set_option(b"raster_dedup", 0))
+        Lb.check(lib.read_set_option(b"raster_nbr_filter", 0))
     for l, (w, h) in enumerate(oracle_mod.level_sizes(W, H, L)):
         gi, gd = ops.zbuf_resolve(pyr, l)
         oi, od = oracle_mod.pcpr_forward(xyz, M, w, h)
