@@ -44,10 +44,14 @@ def allreduce_min_(keys, group=None):
 
 def render_sharded(pyr, xyz_shard, id_base, total_m, group=None):
     """Project this rank's shard into ``pyr`` (cleared here), min-reduce, derive nested levels.
-    After the call every rank holds the identical, complete pyramid."""
+    After the call every rank holds the identical, complete pyramid.  ``xyz_shard``: this rank's slice of the [N,3] cloud
+    (global ids via ``id_base``) or a ``ops.SortedPoints`` shard (a spatial tile; ids travel with the points)."""
     from . import ops
     pyr.clear()
-    ops.raster_project(pyr, xyz_shard, total_m, id_base=id_base, derive=False)
+    if isinstance(xyz_shard, ops.SortedPoints):
+        ops.raster_project_sorted(pyr, xyz_shard, total_m)
+    else:
+        ops.raster_project(pyr, xyz_shard, total_m, id_base=id_base, derive=False)
     lo, hi = reduce_span(pyr.offsets, pyr.sizes, pyr.B, pyr.direct_levels())
     allreduce_min_(pyr.buf[lo:hi], group)
     ops.raster_derive(pyr)

@@ -101,14 +101,30 @@ class SortedPoints:
         self.pts4 = pts4
 
 
+    def shard(self, start, count):
+        """Rows [start, start+count) of the sorted store as a store of their own: a contiguous range of the Morton order
+        is a compact spatial tile of the scene (the multi-GPU partition)."""
+        sub = object.__new__(SortedPoints)
+        sub.n, sub.cell = int(count), self.cell
+        sub.pts4 = self.pts4[start:start + count]
+        sub.perm = self.perm[start:start + count]
+        return sub
+
+
 def raster_project_sorted(pyr, store, total_m):
-    """Level 0 of a cleared single-view pyramid from a SortedPoints store (finish with raster_derive / pyramid_resolve_gather)."""
+    """Level 0 of a cleared pyramid from a SortedPoints store, one launch per view (finish with raster_derive /
+    pyramid_resolve_gather).  total_m: [B,4,4]."""
     L.require_device()
     _f32c(total_m, "total_m")
-    if pyr.B != 1 or total_m.dim() != 3 or total_m.shape[0] != 1:
+    if total_m.dim() != 3 or total_m.shape[0] != pyr.B:
         raise RuntimeError("batch_size check")
-    L.check(L.load().read_raster_project_sorted(store.pts4.data_ptr(), store.n, total_m.data_ptr(), pyr.W, pyr.H, pyr.L,
-                                                pyr.buf.data_ptr(), L.stream_ptr()))
+    if pyr.direct_mask != 1:
+        raise RuntimeError("the sorted-store rasterizer needs nested pyramid levels")
+    lib, sp = L.load(), L.stream_ptr()
+    plane = pyr.W * pyr.H * 8                                    # bytes of one view's level-0 plane
+    for v in range(pyr.B):
+        L.check(lib.read_raster_project_sorted(store.pts4.data_ptr(), store.n, total_m[v].data_ptr(), pyr.W, pyr.H, pyr.L,
+                                               pyr.buf.data_ptr() + v * plane, sp))
 
 
 def raster_derive(pyr):

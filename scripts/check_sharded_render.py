@@ -24,6 +24,12 @@ pyr = ops.Pyramid(world, W, H, L, dev)
 rdist.render_sharded(pyr, torch.from_numpy(xyz[start:start + count]).to(dev), start, m)
 torch.cuda.synchronize()
 ok = torch.equal(pyr.buf, full.buf)
+# the same with spatial tiles: rank r holds the r-th contiguous range of the Morton-sorted store
+store = ops.SortedPoints(torch.from_numpy(xyz).to(dev)).shard(start, count)
+pyr2 = ops.Pyramid(world, W, H, L, dev)
+rdist.render_sharded(pyr2, store, 0, m)
+torch.cuda.synchronize()
+ok = ok and torch.equal(pyr2.buf, full.buf)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
