@@ -411,8 +411,8 @@ def run_ours(args):
     roof_raster = {"kernel": "raster_sorted_kernel + pyramid_resolve_gather_kernel",
                    "bound": "hbm",
                    "achieved": ach_r, "peak": hbm, "unit": "GB/s", "frac": ach_r / hbm, "peak_src": pk["src"],
-                   "traffic": ((traf["raster_lean_kernel_bytes_per_launch"] + traf["pyramid_resolve_gather_bytes_per_launch"])
-                               if traf else None),
+                   "traffic": ((traf.get("raster_sorted_kernel_bytes_per_launch", traf["raster_lean_kernel_bytes_per_launch"])
+                                + traf["pyramid_resolve_gather_bytes_per_launch"]) if traf else None),
                    "algorithmic_bytes": rg_bytes, "ms_per_frame": rg_ms,
                    "note": "algorithmic bytes count 12 B per point (SURVEY 8d); the sorted store holds 16 B per point (xyz + original id)",
                    "project_ms": project_ms, "resolve_gather_ms": resolve_ms}

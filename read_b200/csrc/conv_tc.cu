@@ -37,8 +37,6 @@
 
 namespace rb {
 
-constexpr int TC_THREADS = 384;            // 4 role warps + 8 epilogue warps
-constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_TW = 8, TC_TH = 16;          // 128-pixel M tile: 16 rows of 8 pixels (one 8-row UMMA group per image row)
 constexpr int TC_MAX_STAGES = 16;           // ring depth bounds the bytes in flight per SM (latency-bound small-C layers)
 constexpr uint32_t TC_SMEM_BUDGET = 218 * 1024;

@@ -27,7 +27,6 @@
 namespace rb {
 
 constexpr int G_THREADS = 832;
-constexpr int G_PROD_THREADS = 256;         // warps 2..9
 constexpr int G_EPI_WARP0 = 10;              // warps 10..25
 constexpr int G_EPI_WARPS = 16;
 constexpr int G_TW = 16, G_TH = 8;
@@ -67,7 +66,6 @@ struct GArgs {
     int nacc;                  // TMEM accumulator ring depth (each n_tile columns wide)
     int lean16;                // epilogue work items = (quadrant, 16-column chunk) dealt over tiles (NHWC, Cout 16 / 32 / 64)
     int debug;                 // diagnostic knobs ("tcg_debug"): 1 = epilogue only hand-shakes, 2 = no MMAs, 4 = no gather copies
-    int any_bil;
     uint32_t a_bytes, b_bytes;
     int elu;
     const float *bias_f, *bias_m, *scale, *shift;
@@ -82,7 +80,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // the mbarrier receives one (pre-counted) arrival from this thread once all its prior cp.async have completed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar)
 {
@@ -685,8 +682,6 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
     int stages = (int)(G_SMEM_BUDGET / (a.a_bytes + a.b_bytes));
     if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
     a.stages = stages;
-    a.any_bil = 0;
-    for (int i = 0; i < d.n_src; ++i) a.any_bil |= d.src[i].mode == READ_SRC_BILINEAR_UP4;
     if (stages < 3 || (d.stride != 1 && d.stride != 2)) {
         set_error("tcgen05 gather conv: unsupported geometry (stages %d, stride %d)", stages, d.stride);
         delete p;

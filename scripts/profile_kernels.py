@@ -27,7 +27,9 @@ pyr = ops.Pyramid(1, W, H, LEVELS, dev)
 pyr.clear()
 tex = torch.rand((N, 8), device=dev)
 eng = UNetEngine(synth.synth_state_dict(synth.SEED), 1, H, W, dev, precision="bf16", use_graph=False)
-ops.raster_project(pyr, xyz, m, derive=False)
+store = ops.SortedPoints(xyz)                     # scene load (torch ops, not profiled kernels of ours)
+torch.cuda.synchronize()
+ops.raster_project_sorted(pyr, store, m)          # the frame path's rasterizer
 ops.pyramid_resolve_gather(tex, pyr, eng.inputs, L.FEAT_NHWC_BF16, reset_level0=True)
 torch.cuda.synchronize()
 sp = L.stream_ptr()
