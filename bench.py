@@ -312,7 +312,8 @@ def run_ours(args):
     for s in range(args.warmup):
         resident_step(s)
     torch.cuda.synchronize()
-    launches_per_step = (2 + eng.n_launches()) if world == 1 else (3 + eng.n_launches())   # + NCCL's own kernel
+    # ours: rasterize (one launch per view) + resolve/gather + the net; N > 1 adds the level-0 clear (NCCL's kernel not counted)
+    launches_per_step = (2 + eng.n_launches()) if world == 1 else (2 + B + eng.n_launches())
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
