@@ -68,8 +68,11 @@ class SortedPoints:
     Built once per scene with torch ops on the device (scene load, not the per-frame path)."""
 
     def __init__(self, xyz, cell=0.25):
-        L.require_device()
-        _f32c(xyz, "in_points")
+        # the sort itself is plain torch (runs wherever xyz lives); only the rasterizer needs the device
+        if xyz.dtype != torch.float32:
+            raise RuntimeError("in_points must be a float tensor")
+        if not xyz.is_contiguous():
+            raise RuntimeError("in_points must be contiguous")
         if xyz.dim() != 2 or xyz.shape[1] != 3:
             raise RuntimeError("in_points must be [N,3]")
         n = xyz.shape[0]
@@ -116,6 +119,7 @@ def raster_project_sorted(pyr, store, total_m):
     pyramid_resolve_gather).  total_m: [B,4,4]."""
     L.require_device()
     _f32c(total_m, "total_m")
+    _f32c(store.pts4, "sorted store")
     if total_m.dim() != 3 or total_m.shape[0] != pyr.B:
         raise RuntimeError("batch_size check")
     if pyr.direct_mask != 1:
