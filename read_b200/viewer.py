@@ -35,7 +35,8 @@ class FrameRenderer:
         xyz = torch.as_tensor(np.asarray(xyz, dtype=np.float32) if not torch.is_tensor(xyz) else xyz, dtype=torch.float32)
         self.xyz = xyz.contiguous().to(self.device)
         # scene load: spatially sorted device store (original ids travel with the points), see ops.SortedPoints
-        self.store = ops.SortedPoints(self.xyz) if ops.level_sizes(W, H, n_levels) == [(W >> l, H >> l) for l in range(n_levels)] else None
+        nested = L.load().read_raster_direct_mask(W, H, n_levels) == 1        # every level exactly half of the previous one
+        self.store = ops.SortedPoints(self.xyz) if nested else None
         net = UNet()
         net.load_state_dict(net_state_dict, strict=True)
         if not isinstance(texture, PointTexture):
