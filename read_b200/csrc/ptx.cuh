@@ -97,6 +97,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has COMPLETED and its
+// memory is visible (a no-op for a normally launched kernel), pdl_launch_dependents() lets the successor's CTAs be scheduled
+// as soon as resources free up (their prologue - barrier init, TMEM alloc, weight loads - overlaps our tail).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

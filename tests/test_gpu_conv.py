@@ -181,6 +181,11 @@ TC_CASES = [
     ("persistent C32, 2560 tiles (17 per CTA)", [(32, 512, 640, "id", 1)], 32, 3, True, {}),
     ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
     ("final layer 32->3, NCHW f32 output", [(32, 24, 40, "id", 1)], 3, 3, False, {"final": True}),
+    # the C3 shapes of the streamed-weight instances (B = 2): the B ring and the accumulator ring wrap many times per CTA
+    ("persistent C128 @272x480 + residual (Encoder.2 at C3), 14 tiles per CTA", [(128, 272, 480, "id", 1)], 128, 3, False, {"residual": True}),
+    ("persistent C128 @272x480 ELU", [(128, 272, 480, "id", 1)], 128, 3, True, {}),
+    ("persistent C256 @136x240 + residual (Encoder.3 at C3), two n-tiles", [(256, 136, 240, "id", 1)], 256, 3, False, {"residual": True}),
+    ("persistent C256 @136x240 ELU", [(256, 136, 240, "id", 1)], 256, 3, True, {}),
     # stride 2 on the TMA path: four phase tiles per stage (even / odd input columns x rows), traversal-stride-2 TMA loads
     ("3x3 s2 32->64 + FAM product output (feat_extract.1)", [(32, 32, 48, "id", 1)], 64, 3, True, {"stride": 2, "out2": True}),
     ("3x3 s2 64->128 ragged tiles (feat_extract.2)", [(64, 38, 26, "id", 1)], 128, 3, True, {"stride": 2, "out2": True}),
