@@ -37,8 +37,14 @@ enum {
 
 int read_version(void);
 const char *read_last_error(void);
-/* Tuning / debugging knobs (results are identical for every setting): "raster_pipelined" (default 1),
- * "raster_bulk_tma" (default 1). */
+/* Tuning options.  Results are bit-identical for every accepted setting; unknown names and out-of-range values are rejected.
+ *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = query),
+ *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0)
+ *   convs:      "tc_mt" (supertile width, 0 = auto / 1 / 2 / 4; read when a plan is created), "tc_role_rot" (1),
+ *               "tc_pdl" (1: programmatic dependent launch between consecutive conv kernels)
+ * The options are process-wide tuning state (plain ints): set them before creating plans / launching, not concurrently with
+ * launches from other threads.  Diagnostic knobs that skip work and therefore corrupt the output ("tc_debug", "tcg_debug",
+ * raster_mode 4 / 5) exist only in builds compiled with -DREAD_DIAG and are absent from the shipped library. */
 int read_set_option(const char *name, int value);
 /* 1 if the current device is sm_100 (B200); the library refuses to launch elsewhere. */
 int read_device_ok(void);
@@ -85,6 +91,10 @@ int read_raster_derive_levels(int B, int W, int H, int L, uint64_t *zbuf, void *
  * (depth | original id) keys, hence identical to read_raster_project_direct on the unsorted cloud. */
 int read_raster_project_sorted(const float *pts4, int64_t n, const float *total_m, int W, int H, int L, uint64_t *zbuf,
                                void *stream);
+/* Same for B <= 8 views in ONE pass over the store (total_m [B,16]; view b goes to level 0 of view b of a B-view pyramid,
+ * i.e. zbuf + b*W*H): the multi-GPU frame path, where every rank rasterises its spatial tile for all views of the step. */
+int read_raster_project_sorted_views(const float *pts4, int64_t n, const float *total_m, int B, int W, int H, int L,
+                                     uint64_t *zbuf, void *stream);
 /* Bitmask of levels rasterised with direct atomics (bit l set) for this geometry. */
 unsigned read_raster_direct_mask(int W, int H, int L);
 
@@ -225,6 +235,13 @@ int read_upsample_bilinear4(const void *in, int act_dtype, int B, int h, int w, 
 /* Viewer output path (replaces READ/gl/nn.py:123-124 `permute + cat alpha` and the flip of viewer.py:267):
  * RGB planes [3,H,W] f32 -> [H,W,4] f32 (alpha constant), optionally flipped vertically. */
 int read_frame_to_rgba(const float *rgb_planes, int H, int W, int flip_vertical, float alpha, float *out_hwc4, void *stream);
+
+/* Net-input staging for NetAndTexture's viewer options on the fused path (READ/models/compose.py:162-171): src = f32 NHWC
+ * features [B,hs,ws,C] at render resolution; factor = supersampling (bilinear reduce exactly as F.interpolate(scale_factor=1/ss,
+ * mode='bilinear')); last (nullable) = f32 [B,hs/factor,ws/factor,C] temporal-average state: out = (cur + last) / 2 when
+ * have_last, and last := out; dst = NHWC in act_dtype (the engine's input buffer). */
+int read_stage_net_inputs(const float *src, int B, int hs, int ws, int C, int factor, float *last, int have_last, int act_dtype,
+                          void *dst, void *stream);
 
 int read_nchw_f32_to_nhwc(const float *in, int B, int C, int H, int W, int act_dtype, void *out, void *stream);
 int read_nhwc_to_nchw_f32(const void *in, int act_dtype, int B, int C, int H, int W, float *out, void *stream);

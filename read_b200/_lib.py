@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libread_b200.so")
+# READ_B200_LIB: timing-experiment scripts point this at the -DREAD_DIAG build (python -m read_b200.build --diag)
+LIB_PATH = os.environ.get("READ_B200_LIB") or os.path.join(_HERE, "libread_b200.so")
 
 c_int, c_i64, c_u32 = ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
 c_vp = ctypes.c_void_p
@@ -56,6 +57,8 @@ _SIGS = {
     "read_raster_project_direct": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_derive_levels": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_sorted": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_raster_project_sorted_views": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_stage_net_inputs": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]),
     "read_raster_direct_mask": (c_u32, [c_int, c_int, c_int]),
     "read_zbuf_resolve": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "read_pcpr_forward": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

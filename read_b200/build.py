@@ -33,16 +33,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, diag=False):
+    """diag=True builds libread_b200_diag.so with -DREAD_DIAG (work-skipping knobs + role timelines for timing experiments;
+    never loaded by the product: scripts opt in with READ_B200_LIB=...)."""
+    if diag:
+        return _build(LIB.replace(".so", "_diag.so"), "_obj_diag", ["-DREAD_DIAG"], verbose)
     if not force and not _stale():
         return LIB
+    return _build(LIB, "_obj", [], verbose)
+
+
+def _build(LIB, objdir, extra, verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, objdir), exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "_obj", os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(HERE, objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -59,4 +67,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv))

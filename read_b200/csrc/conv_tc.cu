@@ -41,8 +41,17 @@ namespace rb {
 // the shipped library compiles them out (scripts/tc_debug_times.py builds its own copy).
 #ifdef READ_DIAG
 #define TC_DBG(a_, bit_) (((a_).debug & (bit_)) != 0)
+// per-role timeline of CTA 0: trace[role * 2048 + 1 + i] = (code << 56) | clock64, trace[role * 2048] = count
+#define TC_TRACE(role_, code_)                                                                                          \
+    do {                                                                                                                \
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trc_n < 2046u) {                                      \
+            a.trace[(role_) * 2048 + 1 + trc_n] = ((unsigned long long)(code_) << 56) | ((unsigned long long)clock64() & 0x00FFFFFFFFFFFFFFull); \
+            a.trace[(role_) * 2048] = ++trc_n;                                                                          \
+        }                                                                                                               \
+    } while (0)
 #else
 #define TC_DBG(a_, bit_) false
+#define TC_TRACE(role_, code_) do { } while (0)
 #endif
 
 constexpr int TC_TW = 8, TC_TH = 16;          // 128-pixel M tile: 16 rows of 8 pixels (one 8-row UMMA group per image row)
@@ -94,10 +103,16 @@ struct TcArgs {
     int raw;                              // RAW output: store the accumulators themselves, [.., n_tile] channels
     int mt;                               // M tiles per SUPERTILE (1, 2 or 4 horizontally adjacent 8x16-pixel tiles share ONE halo load,
                                           // one ring stage and one set of hand-shakes; each keeps its own TMEM accumulator slot)
+    int mt_log2, nacc_log2;
     int stiles_x;                         // supertiles per image row: ceil(tiles_x / mt)
     float inv_stx;
     int role_rot;                         // 1: the single-issuer roles (TMA producers, MMA issuers) run in the HIGHEST warp ids
     int pdl;                              // launched with programmatic stream serialization (griddepcontrol in the kernel)
+    int commit_late;                      // supertiles: commit the M tiles' tfull barriers together at the end of the supertile
+    int merge_done;                       // resident weights, kchunks == 1, mt == 1: ONE "tile done" commit per tile - the producers wait
+                                          // on the accumulator's tfull barrier (A stage j of issuer me <-> accumulator slot 2j + me)
+    int bpair;                            // streamed weights: one tcgen05.commit per PAIR of B stages
+    unsigned long long *trace;            // READ_DIAG builds: per-role timeline buffer (see TC_TRACE), else null
 };
 
 // tile index -> (n tile, tile x, tile y, image) without integer division: fdiv_small, conv_common.cuh
@@ -115,6 +130,17 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const TcArgs &a)
     // mt indexes SUPERTILES; tx is the x index of the supertile's first M tile
     const int q = fdiv_small(mt, a.inv_stx);
     c.tx = (mt - q * a.stiles_x) * a.mt;
+    c.b = fdiv_small(q, a.inv_ty);
+    c.ty = q - c.b * a.tiles_y;
+    return c;
+}
+// same for layers with a single n tile (work unit == supertile)
+__device__ __forceinline__ TileCoord decode_supertile(int s, const TcArgs &a)
+{
+    TileCoord c;
+    c.nt = 0;
+    const int q = fdiv_small(s, a.inv_stx);
+    c.tx = (s - q * a.stiles_x) * a.mt;
     c.b = fdiv_small(q, a.inv_ty);
     c.ty = q - c.b * a.tiles_y;
     return c;
@@ -179,6 +205,9 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int warp = a.role_rot ? (int)(((threadIdx.x >> 5) + 4u) % (NTHR / 32)) : (int)(threadIdx.x >> 5);
     if (a.pdl) pdl_launch_dependents();
+#ifdef READ_DIAG
+    unsigned trc_n = 0;
+#endif
 
     for (int i = threadIdx.x; i < a.cout_pad; i += NTHR) {
         // one float4 per channel: {bias_f, bias_m, bn_scale, bn_shift} -> a single LDS.128 in the epilogue
@@ -251,7 +280,9 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             __syncwarp();
             for (int kc = 0; kc < a.kchunks; ++kc) {
                 const uint32_t slot = ring_base + as;
-                mbar_wait(aempty0 + 8 * slot, aph ^ 1u);
+                // merged mode: the stage is free when the tile that used it is complete = its accumulator's tfull barrier
+                mbar_wait(a.merge_done ? tfull0 + 8 * (a.dual ? 2u * as + pme : as) : aempty0 + 8 * slot, aph ^ 1u);
+                TC_TRACE(pme, 1);
                 if (elect_one()) {
                     if (TC_DBG(a, 4)) {
                         mbar_arrive(afull0 + 8 * slot);
@@ -281,6 +312,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                     }
                 }
                 __syncwarp();
+                TC_TRACE(pme, 2);
                 if (++as == ring_n) { as = 0; aph ^= 1u; }
                 if (!RES) {
 #pragma unroll
@@ -288,7 +320,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                         int row = (kx * a.kchunks + kc) * n_total + nt * a.n_tile;       // tap = ky*KS + kx
 #pragma unroll
                         for (int ky = 0; ky < KS; ++ky, row += row_step) {
-                            mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+                            mbar_wait(bempty0 + 8 * (a.bpair ? (bs | 1u) : bs), bph ^ 1u);   // pair mode: the pair's (odd) barrier
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(bfull0 + 8 * bs, a.b_bytes);
                                 tma_load_2d(&tmB, bfull0 + 8 * bs, b_addr, 0, row);
@@ -346,11 +378,13 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             if (acc_c >= (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
             if (a.dual ? ((tile_it & 1u) != me) : (me != 0u)) continue;   // not this issuer's supertile
             for (uint32_t mi = 0; mi < MT; ++mi) mbar_wait(tempty0 + 8 * (acc + mi), acc_ph ^ 1u);
+            TC_TRACE(2 + me, 3);
             tcgen05_fence_after();
             const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)a.n_tile;
             uint32_t bkc = b_lo0;                                      // resident weights: chunk kc of tap 0
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
                 mbar_wait(afull0 + 8 * (ring_bar + as), aph);
+                TC_TRACE(2 + me, 4);
                 tcgen05_fence_after();
                 const bool last_kc = kc == a.kchunks - 1;
                 if (RES) {
@@ -374,9 +408,11 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                                     }
                                 }
                             }
-                            if (last_kc) umma_commit(tfull0 + 8 * (acc + mi));    // this M tile's accumulator is complete
+                            if (last_kc && !a.commit_late) umma_commit(tfull0 + 8 * (acc + mi));    // this M tile's accumulator is complete
                         }
-                        umma_commit(aempty0 + 8 * (ring_bar + as));
+                        if (last_kc && a.commit_late)
+                            for (uint32_t mi = 0; mi < MT; ++mi) umma_commit(tfull0 + 8 * (acc + mi));
+                        if (!a.merge_done) umma_commit(aempty0 + 8 * (ring_bar + as));
                     }
                     __syncwarp();
                 } else {
@@ -398,7 +434,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                                         umma_bf16_lohi2(d_tmem, al + 2u * kk, desc_hi, b_lo + 2u * kk, desc_hi_b, idesc, accum);
                                     }
                                 }
-                                umma_commit(bempty0 + 8 * bs);
+                                if (!a.bpair || (bs & 1u)) umma_commit(bempty0 + 8 * bs);
                             }
                             __syncwarp();
                             b_lo += b16;
@@ -412,6 +448,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                     }
                     __syncwarp();
                 }
+                TC_TRACE(2 + me, 5);
                 a_lo += st16;
                 if (++as == ring_n) { as = 0; aph ^= 1u; a_lo = ring_lo0; }
             }
@@ -427,8 +464,124 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         const int half = a.n_tile >> 1;
         const int nchunks = half >> 4;
         const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
-        uint32_t acc_c = 0, acc_p = 0, lean_it = 0;
+        uint32_t acc_c = 0, acc_p = 0;
         if (a.pdl) pdl_wait();        // residual / add-in / FAM-multiplier tensors come from earlier kernels
+        if (NTHR == 640 && (EPI != 0 || !a.raw)) {
+            // ---------------- lean 16-warp item loop (Cout 16 / 32 / 64, one n tile) ----------------
+            // Work item = (TMEM lane quadrant q, 16-column chunk) of one M tile: 4 * nch16 items per tile.  Warp -> (q, chunk)
+            // is FIXED; with nch16 = 1 / 2 / 4 chunks per tile a warp serves every 4th / 2nd / every M tile of the CTA's
+            // sequence.  A lane owns 32 contiguous output bytes of its pixel (full sectors for the residual read and the store).
+            // Round-2 role timelines (profiles/r02_role_timelines.md) showed the epilogue - not the tensor pipe - bounding the
+            // C=32 / C=64 layers, and the epilogue itself issue-bound: ~560 warp instructions per item of which only 180 were
+            // the 16 outputs' math; the rest was the per-tile header (tile decode, 64-bit offsets, ring bookkeeping) executed
+            // by EVERY warp for EVERY tile, including the tiles it skips.  This loop visits only the warp's own items and
+            // derives tile / accumulator slot / phase from the item index with shifts.
+            // EPI fixes the layer kind at compile time (1: ELU, no residual - ResBlock main.0; 2: no activation + residual -
+            // ResBlock main.1; 0: runtime flags).
+            const bool elu = EPI == 1 ? true : (EPI == 2 ? false : a.elu != 0);
+            const bool has_res = EPI == 2 ? true : (EPI == 1 ? false : a.residual != nullptr);
+            const bool has_out2 = EPI != 0 ? false : a.out2 != nullptr;
+            const int nch16 = half >> 4;                       // 1, 2 or 4 (host: lean only for Cout 16 / 32 / 64)
+            const int lg = nch16 >> 1;                         // log2(nch16)
+            const int chunk = sub & (nch16 - 1);
+            const uint32_t item_step = 4u >> lg;               // M tiles between two items of this warp
+            const uint32_t n_units = (uint32_t)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // this CTA's supertiles
+            const uint32_t n_mtiles = n_units << a.mt_log2;
+            for (uint32_t it = (uint32_t)sub >> lg; it < n_mtiles; it += item_step) {
+                const uint32_t su = it >> a.mt_log2, mi = it & (uint32_t)(a.mt - 1);
+                const TileCoord tc_ = decode_supertile((int)(blockIdx.x + su * gridDim.x), a);
+                const int b = tc_.b;
+                const int x = (tc_.tx + (int)mi) * TC_TW + px, y = tc_.ty * TC_TH + py;
+                const bool inside = (x < a.W) && (y < a.H);
+                const uint32_t acc = it & (uint32_t)(a.nacc - 1), acc_ph = (it >> a.nacc_log2) & 1u;   // nacc is a power of two
+                const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
+                const int co = chunk * 16;                                              // lean layers have ONE n tile
+                const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;                  // < 2^31 (checked by the host)
+                uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, ml0 = rs0, ml1 = rs0;
+                uint4 af0 = rs0, af1 = rs0, am0 = rs0, am1 = rs0;            // add-in: f and m columns of this item
+                const bool has_addin = EPI == 0 && a.addin != nullptr;
+                if (has_addin && inside) {
+                    const __nv_bfloat16 *ap = a.addin + ((b * a.addin_H + (y >> 1)) * a.addin_W + (x >> 1)) * a.n_tile + chunk * 16;
+                    af0 = __ldg(reinterpret_cast<const uint4 *>(ap));
+                    af1 = __ldg(reinterpret_cast<const uint4 *>(ap) + 1);
+                    am0 = __ldg(reinterpret_cast<const uint4 *>(ap + half));
+                    am1 = __ldg(reinterpret_cast<const uint4 *>(ap + half) + 1);
+                }
+                if (inside) {
+                    if (has_res) {
+                        rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                        rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                    }
+                    if (has_out2) {
+                        ml0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
+                        ml1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
+                    }
+                }
+                TC_TRACE(warp, 9);
+                mbar_wait(tfull0 + 8 * acc, acc_ph);
+                TC_TRACE(warp, 6);
+                tcgen05_fence_after();
+                uint32_t f16[16], m16[16];
+                tmem_ld16(trow + (uint32_t)(chunk * 16), f16);
+                tmem_ld16(trow + (uint32_t)(half + chunk * 16), m16);
+                tmem_ld_wait();
+                TC_TRACE(warp, 7);
+                // the accumulator is in registers: hand the TMEM slot back before the math
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (has_addin) {        // pre-activation terms computed at the coarser resolution (nearest x2)
+                    const uint32_t fa[8] = {af0.x, af0.y, af0.z, af0.w, af1.x, af1.y, af1.z, af1.w};
+                    const uint32_t ma[8] = {am0.x, am0.y, am0.z, am0.w, am1.x, am1.y, am1.z, am1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f16[2 * j] = __float_as_uint(__uint_as_float(f16[2 * j]) + __uint_as_float(fa[j] << 16));
+                        f16[2 * j + 1] = __float_as_uint(__uint_as_float(f16[2 * j + 1]) + __uint_as_float(fa[j] & 0xFFFF0000u));
+                        m16[2 * j] = __float_as_uint(__uint_as_float(m16[2 * j]) + __uint_as_float(ma[j] << 16));
+                        m16[2 * j + 1] = __float_as_uint(__uint_as_float(m16[2 * j + 1]) + __uint_as_float(ma[j] & 0xFFFF0000u));
+                    }
+                }
+                float yv[16];
+                if (elu) {              // warp-uniform: the no-activation layers skip the ex2 path entirely
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<true>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
+                }
+                if (inside) {
+                    if (has_res) {
+                        const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            yv[2 * j] += __uint_as_float(rr[j] << 16);
+                            yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = cvt_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                    uint4 *op = reinterpret_cast<uint4 *>(a.out + o);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (has_out2) {
+                        const uint32_t mm[8] = {ml0.x, ml0.y, ml0.z, ml0.w, ml1.x, ml1.y, ml1.z, ml1.w};
+                        uint32_t p2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
+                            const float2 mv = unpack_bf16x2(mm[j]);
+                            p2[j] = cvt_bf16x2(ys.x * mv.x, ys.y * mv.y);
+                        }
+                        uint4 *o2 = reinterpret_cast<uint4 *>(a.out2 + o);
+                        o2[0] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        o2[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
+                    }
+                }
+                TC_TRACE(warp, 8);
+                TC_TRACE(warp, 8);
+            }
+        } else
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x)
         for (int mi = 0; mi < a.mt; ++mi) {                           // the M tiles of the supertile, one accumulator slot each
             const TileCoord tc_ = decode_tile(t, a);
@@ -506,102 +659,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                     continue;
                 }
-                const bool elu = EPI == 1 ? true : (EPI == 2 ? false : a.elu != 0);
-                const bool has_res = EPI == 2 ? true : (EPI == 1 ? false : a.residual != nullptr);
-                const bool has_out2 = EPI != 0 ? false : a.out2 != nullptr;
-                const int nch16 = half >> 4;                       // 1, 2 or 4 (host: lean only for Cout 16 / 32 / 64)
-                const int kq = sub;                                // (warp - 4) >> 2
-                const int chunk = kq & (nch16 - 1);
-                if (((lean_it++) & (uint32_t)((4 >> (nch16 >> 1)) - 1)) != (uint32_t)(kq >> (nch16 >> 1))) continue;   // not my tile
-                if (TC_DBG(a, 1)) {
-                    mbar_wait(tfull0 + 8 * acc, acc_ph);
-                    tcgen05_fence_after();
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                    continue;
-                }
-                const bool mem_ok = !TC_DBG(a, 8);
-                const int co = nt * half + chunk * 16;
-                const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;                  // < 2^31 (checked by the host)
-                uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, ml0 = rs0, ml1 = rs0;
-                uint4 af0 = rs0, af1 = rs0, am0 = rs0, am1 = rs0;            // add-in: f and m columns of this item
-                const bool has_addin = EPI == 0 && a.addin != nullptr;
-                if (has_addin && inside && mem_ok) {
-                    const __nv_bfloat16 *ap = a.addin + ((b * a.addin_H + (y >> 1)) * a.addin_W + (x >> 1)) * a.n_tile + chunk * 16;
-                    af0 = __ldg(reinterpret_cast<const uint4 *>(ap));
-                    af1 = __ldg(reinterpret_cast<const uint4 *>(ap) + 1);
-                    am0 = __ldg(reinterpret_cast<const uint4 *>(ap + half));
-                    am1 = __ldg(reinterpret_cast<const uint4 *>(ap + half) + 1);
-                }
-                if (inside && mem_ok) {
-                    if (has_res) {
-                        rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
-                        rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
-                    }
-                    if (has_out2) {
-                        ml0 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o));
-                        ml1 = __ldg(reinterpret_cast<const uint4 *>(a.out2_mul + o) + 1);
-                    }
-                }
-                mbar_wait(tfull0 + 8 * acc, acc_ph);
-                tcgen05_fence_after();
-                uint32_t f16[16], m16[16];
-                tmem_ld16(trow + (uint32_t)(chunk * 16), f16);
-                tmem_ld16(trow + (uint32_t)(half + chunk * 16), m16);
-                tmem_ld_wait();
-                // the accumulator is in registers: hand the TMEM slot back before the math
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                if (has_addin) {        // pre-activation terms computed at the coarser resolution (nearest x2)
-                    const uint32_t fa[8] = {af0.x, af0.y, af0.z, af0.w, af1.x, af1.y, af1.z, af1.w};
-                    const uint32_t ma[8] = {am0.x, am0.y, am0.z, am0.w, am1.x, am1.y, am1.z, am1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        f16[2 * j] = __float_as_uint(__uint_as_float(f16[2 * j]) + __uint_as_float(fa[j] << 16));
-                        f16[2 * j + 1] = __float_as_uint(__uint_as_float(f16[2 * j + 1]) + __uint_as_float(fa[j] & 0xFFFF0000u));
-                        m16[2 * j] = __float_as_uint(__uint_as_float(m16[2 * j]) + __uint_as_float(ma[j] << 16));
-                        m16[2 * j + 1] = __float_as_uint(__uint_as_float(m16[2 * j + 1]) + __uint_as_float(ma[j] & 0xFFFF0000u));
-                    }
-                }
-                float yv[16];
-                if (elu) {              // warp-uniform: the no-activation layers skip the ex2 path entirely
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<true>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
-                }
-                if (inside && (mem_ok || yv[0] == 123.456f)) {
-                    if (has_res) {
-                        const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            yv[2 * j] += __uint_as_float(rr[j] << 16);
-                            yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
-                        }
-                    }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = cvt_bf16x2(yv[2 * j], yv[2 * j + 1]);
-                    uint4 *op = reinterpret_cast<uint4 *>(a.out + o);
-                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    if (has_out2) {
-                        const uint32_t mm[8] = {ml0.x, ml0.y, ml0.z, ml0.w, ml1.x, ml1.y, ml1.z, ml1.w};
-                        uint32_t p2[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 ys = unpack_bf16x2(pk[j]);   // the stored (rounded) activation
-                            const float2 mv = unpack_bf16x2(mm[j]);
-                            p2[j] = cvt_bf16x2(ys.x * mv.x, ys.y * mv.y);
-                        }
-                        uint4 *o2 = reinterpret_cast<uint4 *>(a.out2 + o);
-                        o2[0] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                        o2[1] = make_uint4(p2[4], p2[5], p2[6], p2[7]);
-                    }
-                }
+                // (the gated lean items are served by the item loop above; only RAW terms reach this point)
                 continue;
             }
             // two statically named register buffers (A/B): runtime-indexed arrays would be demoted to local memory
@@ -733,6 +791,7 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
 struct TcGeom {
     int cin_blk, kchunks, n_tile, n_tiles, cout_pad;
 };
+int g_tc_commit_late = 0, g_tc_merge_done = 0, g_tc_bpair = 0;     // experiments (read_set_option), read at plan creation
 int g_tc_mt = 0;          // supertile width override (read_set_option "tc_mt"): 0 = auto, 1 / 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
 static int desc_chan_gran(const read_conv_desc &d)
@@ -867,14 +926,16 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     int mt = 1;
     if (!s2 && g.n_tiles == 1) {
         const uint32_t total_b0 = (uint32_t)(d.k * d.k * g.kchunks) * (uint32_t)g.n_tile * g.cin_blk * 2u;
+        const uint32_t ab1 = (((uint32_t)halo_rows * (uint32_t)(TC_TW + d.k - 1) * g.cin_blk * 2u) + 1023u) & ~1023u;
+        const bool res1 = total_b0 <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b0 >= 2 * ab1;   // resident weights at mt 1
         for (int cand = 4; cand >= 2; cand >>= 1) {
             if (g_tc_mt > 0 && cand != g_tc_mt) continue;
             if (cand * g.n_tile > 256 || nacc0 % cand != 0) continue;
             if (g_tc_mt <= 0 && tiles_x0 < 4 * cand) continue;
             const uint32_t ab = (((uint32_t)halo_rows * (uint32_t)(TC_TW * cand + d.k - 1) * g.cin_blk * 2u) + 1023u) & ~1023u;
-            const bool res = total_b0 <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b0 >= 2 * ab;
-            if (res ? ((TC_SMEM_BUDGET - total_b0) / ab < (uint32_t)(4 * g.kchunks))
-                    : (3 * ab + 4u * (uint32_t)g.n_tile * g.cin_blk * 2u > TC_SMEM_BUDGET)) continue;
+            // never trade resident weights for a wider supertile (the C=64 layers: 144 KB of weights leave room for mt 1 only)
+            if (res1 ? ((TC_SMEM_BUDGET - total_b0) / ab < (uint32_t)(4 * g.kchunks))
+                     : (3 * ab + 4u * (uint32_t)g.n_tile * g.cin_blk * 2u > TC_SMEM_BUDGET)) continue;
             mt = cand;
             break;
         }
@@ -923,6 +984,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.tiles_x = (d.Wout + TC_TW - 1) / TC_TW;
     a.tiles_y = (d.Hout + TC_TH - 1) / TC_TH;
     a.mt = mt;
+    a.mt_log2 = mt == 4 ? 2 : (mt == 2 ? 1 : 0);
     a.stiles_x = (a.tiles_x + mt - 1) / mt;
     a.inv_stx = 1.0f / (float)a.stiles_x;
     a.halo_w = halo_w;
@@ -967,8 +1029,23 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.inv_tx = 1.0f / (float)a.tiles_x;
     a.inv_ty = 1.0f / (float)a.tiles_y;
     a.nacc = TC_TMEM_COLS / g.n_tile > TC_MAX_ACC ? TC_MAX_ACC : TC_TMEM_COLS / g.n_tile;
+    a.nacc_log2 = 0;
+    while ((1 << a.nacc_log2) < a.nacc) ++a.nacc_log2;     // n_tile is 16 * 2^k here: nacc is 2, 4 or 8
     a.dual = (a.b_resident && a.a_stages >= 4 * g.kchunks) ? 1 : 0;      // >= 2 tiles of A per issuer
     if (a.dual) a.a_stages &= ~1;            // two equal half rings
+    a.commit_late = g_tc_commit_late ? 1 : 0;
+    a.merge_done = 0;
+    if (g_tc_merge_done && a.b_resident && g.kchunks == 1 && mt == 1 && a.a_stages >= a.nacc) {
+        a.merge_done = 1;                    // A ring depth == accumulator ring depth: stage <-> slot is one-to-one
+        a.a_stages = a.nacc;
+        a.dual = a.nacc >= 4 ? 1 : 0;
+    }
+    a.bpair = 0;
+    if (g_tc_bpair && !a.b_resident && a.b_stages >= 4) {
+        a.bpair = 1;
+        a.b_stages &= ~1;
+        b_region_bytes = (uint32_t)a.b_stages * a.b_bytes;
+    }
     a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
@@ -986,6 +1063,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
 }
 
 int g_tc_debug = 0;
+unsigned long long *g_tc_trace = nullptr;    // READ_DIAG builds only (read_set_trace_buffer)
 int g_tc_role_rot = 1;    // single-issuer roles in the highest warp ids (read_set_option "tc_role_rot")
 int g_tc_pdl = 1;         // programmatic dependent launch between consecutive conv kernels (read_set_option "tc_pdl")
 
@@ -995,6 +1073,7 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     a.debug = g_tc_debug;
     a.role_rot = g_tc_role_rot ? 1 : 0;
     a.pdl = g_tc_pdl ? 1 : 0;
+    a.trace = g_tc_trace;
     const long long total_tiles = (long long)a.stiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
@@ -1070,6 +1149,10 @@ static int pack_tc_impl(const float *wf, const float *wm, int Cout, int Cin, int
                         void *stream);
 
 extern "C" {
+
+#ifdef READ_DIAG
+void read_set_trace_buffer(void *buf) { g_tc_trace = static_cast<unsigned long long *>(buf); }
+#endif
 
 int64_t read_tc_weight_elems(int Cout, int Cin, int k)
 {

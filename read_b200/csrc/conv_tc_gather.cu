@@ -26,6 +26,12 @@
 
 namespace rb {
 
+#ifdef READ_DIAG
+#define TCG_DBG(a_, bit_) (((a_).debug & (bit_)) != 0)
+#else
+#define TCG_DBG(a_, bit_) false
+#endif
+
 constexpr int G_THREADS = 832;
 constexpr int G_EPI_WARP0 = 10;              // warps 10..25
 constexpr int G_EPI_WARPS = 16;
@@ -64,6 +70,7 @@ struct GArgs {
     float inv_tx, inv_ty, inv_nt;   // reciprocals for the division-free tile decode
     int stages;
     int nacc;                  // TMEM accumulator ring depth (each n_tile columns wide)
+    int pdl;                   // launched with programmatic stream serialization
     int lean16;                // epilogue work items = (quadrant, 16-column chunk) dealt over tiles (NHWC, Cout 16 / 32 / 64)
     int debug;                 // diagnostic knobs ("tcg_debug"): 1 = epilogue only hand-shakes, 2 = no MMAs, 4 = no gather copies
     uint32_t a_bytes, b_bytes;
@@ -156,6 +163,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CP = a.Cout_pad;
+    if (a.pdl) pdl_launch_dependents();
     // per-(K block, 16-byte chunk) decode table, built once per CTA so the producers' hot loop has no division:
     // {source index (-1 = zero padding of K), ky, kx, channel offset inside the source}
     int4 *s_tab = reinterpret_cast<int4 *>(s_par4 + CP);
@@ -206,6 +214,9 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above touched only static data (weights' descriptors, folded constants): with programmatic dependent launch
+    // it overlapped the previous kernel's tail; activations / residuals below need that kernel to have completed
+    if (a.pdl) pdl_wait();
 
     const int m_tiles = a.tiles_x * a.tiles_y * a.B;
     const long long total_tiles = (long long)m_tiles * a.n_tiles;
@@ -255,7 +266,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                     tcgen05_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < G_KBLK / 16; ++kk) {
-                        if (a.debug & 2) continue;
+                        if (TCG_DBG(a, 2)) continue;
                         umma_bf16_lohi(d_tmem, lo + 2u * kk, lo + ab16 + 2u * kk, desc_hi, idesc,
                                        kk != 0 ? 1u : (kb != 0 ? 1u : 0u));
                     }
@@ -296,7 +307,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 if (s == w) {
                     mbar_wait(my_empty, ph ^ 1u);
                     const uint32_t dst0 = smem_base + s * stage_bytes;
-                    if (a.debug & 4) {
+                    if (TCG_DBG(a, 4)) {
                         mbar_arrive(full0 + 8 * s);
                     } else {
                         const int4 e = tab[kb * 8];
@@ -395,7 +406,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
                 mbar_wait(tfull0 + 8 * acc, acc_ph);
                 tcgen05_fence_after();
                 const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
-                if (a.debug & 1) {
+                if (TCG_DBG(a, 1)) {
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -460,7 +471,7 @@ gated_conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             }
             mbar_wait(tfull0 + 8 * acc, acc_ph);
             tcgen05_fence_after();
-            if (a.debug & 1) {
+            if (TCG_DBG(a, 1)) {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -699,6 +710,7 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
 }
 
 int g_tcg_debug = 0;
+extern int g_tc_pdl;
 
 int tcg_plan_launch(const TcgPlan *p, cudaStream_t st)
 {
@@ -708,12 +720,23 @@ int tcg_plan_launch(const TcgPlan *p, cudaStream_t st)
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
     if (grid > total_tiles) grid = total_tiles;
+    a.pdl = g_tc_pdl ? 1 : 0;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lcfg{};
+    lcfg.gridDim = dim3((unsigned)grid);
+    lcfg.blockDim = dim3(G_THREADS);
+    lcfg.dynamicSmemBytes = p->smem_bytes;
+    lcfg.stream = st;
+    lcfg.attrs = lattr;
+    lcfg.numAttrs = a.pdl ? 1 : 0;
     if (a.stride == 1) {
         RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-        gated_conv_tc_gather_kernel<1><<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+        RB_CUDA(cudaLaunchKernelEx(&lcfg, gated_conv_tc_gather_kernel<1>, p->tmB, a));
     } else {
         RB_CUDA(cudaFuncSetAttribute(gated_conv_tc_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-        gated_conv_tc_gather_kernel<2><<<(unsigned)grid, G_THREADS, p->smem_bytes, st>>>(p->tmB, a);
+        RB_CUDA(cudaLaunchKernelEx(&lcfg, gated_conv_tc_gather_kernel<2>, p->tmB, a));
     }
     RB_LAUNCH_CHECK();
     return READ_OK;

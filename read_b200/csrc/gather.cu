@@ -251,6 +251,48 @@ static int launch_gather(const float *tex, int D, long long N, const void *src, 
     return READ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Net-input staging for the two viewer options of NetAndTexture (READ/models/compose.py:162-171) on the fused path:
+//   supersampling ss > 1: the pyramid is rendered at ss x the net resolution and every level's feature map is reduced with
+//     F.interpolate(scale_factor=1/ss, mode='bilinear') (align_corners=False): src = (dst + 0.5) * ss - 0.5, taps i0 = floor(src),
+//     i1 = min(i0 + 1, n - 1), weight src - i0 (even ss: the two central pixels, equal weights; odd ss: the central pixel);
+//   temporal_average: input = (input + last_input) / 2, and the AVERAGED input becomes last_input (compose.py:167-171).
+// One pass: f32 NHWC features at render resolution -> [bilinear reduce] -> [average with / update `last`] -> NHWC act dtype.
+template <typename T>
+__global__ void stage_inputs_kernel(const float *__restrict__ src, int B, int hs, int ws, int C, int factor, float *last,
+                                    int have_last, T *__restrict__ dst)
+{
+    const int hd = hs / factor, wd = ws / factor;
+    const long long total = (long long)B * hd * wd * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int x = (int)(t % wd);
+        t /= wd;
+        const int y = (int)(t % hd);
+        const int b = (int)(t / hd);
+        float v;
+        if (factor == 1) {
+            v = src[i];
+        } else {
+            const float fx = ((float)x + 0.5f) * (float)factor - 0.5f, fy = ((float)y + 0.5f) * (float)factor - 0.5f;
+            const int x0 = (int)fx, y0 = (int)fy;                    // fx, fy >= 0 for factor >= 1
+            const int x1 = x0 + 1 < ws ? x0 + 1 : ws - 1, y1 = y0 + 1 < hs ? y0 + 1 : hs - 1;
+            const float lx = fx - (float)x0, ly = fy - (float)y0;
+            const float *p = src + (long long)b * hs * ws * C + c;
+            const float v00 = p[((long long)y0 * ws + x0) * C], v01 = p[((long long)y0 * ws + x1) * C];
+            const float v10 = p[((long long)y1 * ws + x0) * C], v11 = p[((long long)y1 * ws + x1) * C];
+            // torch's upsample_bilinear2d: w-lerp inside h-lerp, weights (1 - l), l
+            v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        }
+        if (last != nullptr) {
+            if (have_last) v = (v + last[i]) / 2.f;
+            last[i] = v;
+        }
+        dst[i] = from_f32<T>(v);
+    }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -338,6 +380,25 @@ int read_gather_backward(const float *grad_out, const float *ids, int B, int D, 
     if (total == 0) return READ_OK;
     gather_backward_kernel<<<grid_for(total), 256, D * sizeof(float), (cudaStream_t)stream>>>(grad_out, ids, B, D, h, w,
                                                                                                N, grad_tex_nd);
+    RB_LAUNCH_CHECK();
+    return READ_OK;
+}
+
+int read_stage_net_inputs(const float *src, int B, int hs, int ws, int C, int factor, float *last, int have_last, int act_dtype,
+                          void *dst, void *stream)
+{
+    RB_CHECK_ARG(src && dst, "stage_net_inputs: null pointer");
+    RB_CHECK_ARG(B >= 1 && C >= 1 && factor >= 1 && hs >= factor && ws >= factor, "stage_net_inputs: bad shape");
+    RB_CHECK_ARG(hs % factor == 0 && ws % factor == 0, "stage_net_inputs: the render size must be a multiple of the supersampling factor");
+    RB_CHECK_ARG(act_dtype == READ_ACT_F32 || act_dtype == READ_ACT_BF16, "stage_net_inputs: bad act_dtype");
+    const long long total = (long long)B * (hs / factor) * (ws / factor) * C;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    if (act_dtype == READ_ACT_BF16)
+        stage_inputs_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, B, hs, ws, C, factor, last, have_last,
+                                                                                              (__nv_bfloat16 *)dst);
+    else
+        stage_inputs_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, B, hs, ws, C, factor, last, have_last, (float *)dst);
     RB_LAUNCH_CHECK();
     return READ_OK;
 }

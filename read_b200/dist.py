@@ -42,6 +42,25 @@ def allreduce_min_(keys, group=None):
     return keys
 
 
+def reduce_scatter_min_(out, keys, group=None):
+    """Elementwise min across ranks of ``keys`` ([world * n] packed int64 keys: view r's level-0 plane at [r*n, (r+1)*n)), rank r
+    receiving only ITS view's plane in ``out`` [n]: half the bytes of an all-reduce and 1/world of its output traffic
+    (every rank consumes one view).  NCCL: ncclReduceScatter(int64, min); gloo has no reduce-scatter and
+    falls back to all-reduce + slice (host-logic tests only)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out.copy_(keys[:out.numel()])
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert keys.numel() == world * out.numel(), (keys.numel(), world, out.numel())
+    if dist.get_backend(group) == "gloo":
+        tmp = keys.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.MIN, group=group)
+        out.copy_(tmp[rank * out.numel():(rank + 1) * out.numel()])
+    else:
+        dist.reduce_scatter_tensor(out, keys, op=dist.ReduceOp.MIN, group=group)
+    return out
+
+
 def render_sharded(pyr, xyz_shard, id_base, total_m, group=None):
     """Project this rank's shard into ``pyr`` (cleared here), min-reduce, derive nested levels.
     After the call every rank holds the identical, complete pyramid.  ``xyz_shard``: this rank's slice of the [N,3] cloud

@@ -115,8 +115,8 @@ class SortedPoints:
 
 
 def raster_project_sorted(pyr, store, total_m):
-    """Level 0 of a cleared pyramid from a SortedPoints store, one launch per view (finish with raster_derive /
-    pyramid_resolve_gather).  total_m: [B,4,4]."""
+    """Level 0 of a cleared pyramid from a SortedPoints store, all views in one pass over the store (finish with raster_derive /
+    pyramid_resolve_gather).  total_m: [B,4,4] contiguous."""
     L.require_device()
     _f32c(total_m, "total_m")
     _f32c(store.pts4, "sorted store")
@@ -126,9 +126,10 @@ def raster_project_sorted(pyr, store, total_m):
         raise RuntimeError("the sorted-store rasterizer needs nested pyramid levels")
     lib, sp = L.load(), L.stream_ptr()
     plane = pyr.W * pyr.H * 8                                    # bytes of one view's level-0 plane
-    for v in range(pyr.B):
-        L.check(lib.read_raster_project_sorted(store.pts4.data_ptr(), store.n, total_m[v].data_ptr(), pyr.W, pyr.H, pyr.L,
-                                               pyr.buf.data_ptr() + v * plane, sp))
+    for v0 in range(0, pyr.B, 8):                               # one pass over the store per 8 views
+        nb = min(8, pyr.B - v0)
+        L.check(lib.read_raster_project_sorted_views(store.pts4.data_ptr(), store.n, total_m[v0:v0 + nb].data_ptr(), nb, pyr.W,
+                                                     pyr.H, pyr.L, pyr.buf.data_ptr() + v0 * plane, sp))
 
 
 def raster_derive(pyr):

@@ -1,13 +1,19 @@
 """Drop-in for ``READ.pipelines.ogl.TexturePipeline`` (READ/pipelines/ogl.py:58-154) over the B200 kernels.
 
-Use ``--pipeline read_b200.pipeline.TexturePipeline`` with the reference's train.py (the plugin is located
-by dotted path, READ/utils/train.py:148-154), or shadow ``READ.pipelines.ogl``.  Same CLI flags,
-same attributes after ``create`` (model, ds_train, ds_val, optimizer, criterion, net, textures), same
-``state_objects`` / ``dataset_load`` / ``dataset_unload`` / ``extra_optimizer`` / ``get_net`` contract, same
-checkpoint format ({'state_dict','args'}, READ/utils/train.py:42-65).
+Use ``--pipeline read_b200.pipeline.TexturePipeline`` with the reference's train.py (the plugin is located by dotted path,
+READ/utils/train.py:148-154), or shadow ``READ.pipelines.ogl``.  The plugin contract train.py / viewer.py rely
+on, restated here rather than lifted:
 
-Dataset construction (``get_datasets``) and the loss stay the reference's own code: they are outside the render
-hot path and are imported lazily from ``READ`` only in training mode.
+* CLI: ``--descriptor_size --texture_size --texture_ckpt --texture_lr --texture_activation --n_points`` (ogl.py:59-65);
+* after ``create(args)``: ``model`` (NetAndTexture), ``net``, ``textures`` {dataset id -> PointTexture}, ``args`` and - in training
+  mode - ``ds_train``, ``ds_val``, ``optimizer`` (Adam over the net), ``criterion`` (train.py:509-510);
+* ``state_objects()`` -> what gets checkpointed: the net under 'net', each texture under its dataset's name (ogl.py:114-120);
+* ``dataset_load / dataset_unload`` bracket every train / eval epoch, ``extra_optimizer(datasets)`` returns the RMSprop over the
+  descriptors whose learning rate follows the net's schedule (ogl.py:129-144);
+* checkpoints are ``{'state_dict': ..., 'args': ...}`` (READ/utils/train.py:42-65).
+
+Dataset construction (``get_datasets``) and the loss stay the reference's own code: they are outside the render hot path
+ and are imported lazily from ``READ`` only in training mode.
 """
 from pathlib import Path
 
@@ -18,103 +24,113 @@ from .texture import PointTexture
 from .unet import UNet
 from .compose import NetAndTexture
 
-TextureOptimizerClass = optim.RMSprop        # ogl.py:16
+TextureOptimizerClass = optim.RMSprop        # the descriptor optimizer the reference uses (ogl.py:16)
+
+# (flag, kwargs, registered through parser.add - the reference's "also store in the yaml config" alias - or add_argument)
+_CLI = (
+    ('--descriptor_size', dict(type=int, default=8), False),
+    ('--texture_size', dict(type=int), False),
+    ('--texture_ckpt', dict(type=Path), False),
+    ('--texture_lr', dict(type=float, default=1e-1), True),
+    ('--texture_activation', dict(type=str, default='none'), True),
+    ('--n_points', dict(type=int, default=0, help='this is for inference'), True),
+)
 
 
 class Pipeline:
-    """READ/pipelines/pipeline.py:10-31."""
+    """The plugin protocol of READ/pipelines/pipeline.py:10-31: a pipeline must be able to register its flags, build itself from
+    the parsed args and hand out its net; the dataset hooks and the extra optimizer are optional."""
+
+    def _abstract(self, what):
+        raise NotImplementedError(f"{type(self).__name__} must implement {what}()")
 
     def export_args(self, parser):
-        raise NotImplementedError()
+        self._abstract('export_args')
 
     def create(self, args):
-        raise NotImplementedError()
-
-    def dataset_load(self, *args, **kwargs):
-        pass
-
-    def dataset_unload(self, *args, **kwargs):
-        pass
+        self._abstract('create')
 
     def get_net(self):
-        raise NotImplementedError()
+        self._abstract('get_net')
+
+    def dataset_load(self, *args, **kwargs):
+        return None
+
+    def dataset_unload(self, *args, **kwargs):
+        return None
 
     def extra_optimizer(self, *args):
         return None
 
 
 def load_model_checkpoint(path, model):
-    """READ/utils/train.py:60-65."""
-    ckpt = torch.load(path, map_location='cpu')
-    model.load_state_dict(ckpt['state_dict'])
+    """Counterpart of READ/utils/train.py:60-65: restore ``model`` from a ``{'state_dict': ...}`` file."""
+    state = torch.load(path, map_location='cpu')['state_dict']
+    model.load_state_dict(state)
     return model
 
 
 def save_model(save_path, model, args=None):
-    """READ/utils/train.py:42-57 ({'state_dict', 'args'})."""
-    m = model.module if hasattr(model, 'module') else model
-    d = {'state_dict': m.state_dict()}
+    """Counterpart of READ/utils/train.py:42-57: ``{'state_dict': ..., 'args': ...}``; a DataParallel wrapper is looked through."""
+    payload = {'state_dict': getattr(model, 'module', model).state_dict()}
     if args is not None:
-        d['args'] = dict(vars(args)) if hasattr(args, '__dict__') else dict(args)
-    torch.save(d, save_path)
+        payload['args'] = dict(vars(args)) if hasattr(args, '__dict__') else dict(args)
+    torch.save(payload, save_path)
 
 
 def get_net(input_channels, args):
-    return UNet(num_input_channels=8, num_output_channels=3, feature_scale=4, num_res=4)   # ogl.py:19-27
+    """The refinement net of the texture pipeline (ogl.py:19-27): 8 descriptor channels in, RGB out, 4 residual blocks per stage."""
+    return UNet(num_input_channels=8, num_output_channels=3, feature_scale=4, num_res=4)
 
 
 def get_texture(num_channels, size, args):
-    if not hasattr(args, 'reg_weight'):
-        args.reg_weight = 0.
+    """One descriptor set (ogl.py:30-43); ``args.texture_ckpt`` warm-starts it.  Mesh textures are not on the point-cloud path."""
     if getattr(args, 'use_mesh', False):
         raise NotImplementedError("read_b200: mesh textures (MeshTexture) are outside the point-cloud hot path")
+    if not hasattr(args, 'reg_weight'):
+        args.reg_weight = 0.
     texture = PointTexture(num_channels, size, activation=args.texture_activation, reg_weight=args.reg_weight)
-    if getattr(args, 'texture_ckpt', None):
-        texture = load_model_checkpoint(args.texture_ckpt, texture)
-    return texture
+    ckpt = getattr(args, 'texture_ckpt', None)
+    return load_model_checkpoint(ckpt, texture) if ckpt else texture
 
 
 class TexturePipeline(Pipeline):
     def export_args(self, parser):
-        add = getattr(parser, 'add', parser.add_argument)
-        parser.add_argument('--descriptor_size', type=int, default=8)
-        parser.add_argument('--texture_size', type=int)
-        parser.add_argument('--texture_ckpt', type=Path)
-        add('--texture_lr', type=float, default=1e-1)
-        add('--texture_activation', type=str, default='none')
-        add('--n_points', type=int, default=0, help='this is for inference')
+        for flag, kw, via_add in _CLI:
+            (getattr(parser, 'add', parser.add_argument) if via_add else parser.add_argument)(flag, **kw)
 
+    # -------------------------------------------------------------------------------------------- construction
     def create(self, args):
-        if not hasattr(args, 'input_channels'):
-            args.input_channels = None
-        if not args.input_channels:
+        if not getattr(args, 'input_channels', None):                      # older configs do not carry it (ogl.py:46-47,71-72)
             args.input_channels = [args.descriptor_size] * getattr(args, 'num_mipmap', 5)
-        net = get_net(args.input_channels, args)
-        textures = {}
-        if getattr(args, 'inference', False):
-            textures = {0: get_texture(args.descriptor_size, args.n_points, args)}
-        else:
-            from READ.datasets.dynamic import get_datasets          # reference data path, out of scope here
-            self.ds_train, self.ds_val = get_datasets(args)
-            for ds in self.ds_train:
-                assert ds.scene_data['pointcloud'] is not None, 'set pointcloud'
-                size = ds.scene_data['pointcloud']['xyz'].shape[0]
-                textures[ds.id] = get_texture(args.descriptor_size, size, args)
-            self.optimizer = optim.Adam(net.parameters(), lr=args.lr)
-            if len(textures) == 1:
-                self._extra_optimizer = TextureOptimizerClass(textures[0].parameters(), lr=args.texture_lr)
-            else:
-                self._extra_optimizer = None
-            self.criterion = args.criterion_module(**args.criterion_args).cuda()
-        ss = args.supersampling if hasattr(args, 'supersampling') else 1
-        self.net = net
-        self.textures = textures
-        self.model = NetAndTexture(net, textures, ss)
         self.args = args
+        self.net = get_net(args.input_channels, args)
+        if getattr(args, 'inference', False):
+            self.textures = {0: get_texture(args.descriptor_size, args.n_points, args)}
+        else:
+            self.textures = self._create_training_state(args)
+        self.model = NetAndTexture(self.net, self.textures, getattr(args, 'supersampling', 1))
 
+    def _create_training_state(self, args):
+        """Datasets, one texture per scene, both optimizers and the criterion (ogl.py:84-102)."""
+        from READ.datasets.dynamic import get_datasets          # the reference's data path, out of scope here
+        self.ds_train, self.ds_val = get_datasets(args)
+        textures = {}
+        for ds in self.ds_train:
+            cloud = ds.scene_data['pointcloud']
+            assert cloud is not None, 'set pointcloud'
+            textures[ds.id] = get_texture(args.descriptor_size, cloud['xyz'].shape[0], args)
+        self.optimizer = optim.Adam(self.net.parameters(), lr=args.lr)
+        # a single scene keeps ONE descriptor optimizer alive so that its running averages survive across epochs
+        self._extra_optimizer = (TextureOptimizerClass(textures[0].parameters(), lr=args.texture_lr)
+                                 if len(textures) == 1 else None)
+        self.criterion = args.criterion_module(**args.criterion_args).cuda()
+        return textures
+
+    # -------------------------------------------------------------------------------------------- train.py hooks
     def state_objects(self):
-        objs = {'net': self.net}
-        objs.update({ds.name: self.textures[ds.id] for ds in self.ds_train})
+        objs = {ds.name: self.textures[ds.id] for ds in self.ds_train}
+        objs['net'] = self.net
         return objs
 
     def dataset_load(self, dataset):
@@ -122,19 +138,22 @@ class TexturePipeline(Pipeline):
         for ds in dataset:
             ds.load()
 
-    def extra_optimizer(self, dataset):
-        lr_drop = self.optimizer.param_groups[0]['lr'] / self.args.lr
-        if self._extra_optimizer is not None:      # single dataset: keep optimizer state
-            self._extra_optimizer.param_groups[0]['lr'] = self.args.texture_lr * lr_drop
-            return self._extra_optimizer
-        groups = [{'params': self.textures[ds.id].parameters()} for ds in dataset]
-        return TextureOptimizerClass(groups, lr=self.args.texture_lr * lr_drop)
-
     def dataset_unload(self, dataset):
         self.model.unload_textures()
         for ds in dataset:
             ds.unload()
             self.textures[ds.id].null_grad()
+
+    def _texture_lr(self):
+        """texture_lr scaled by however far the net's schedule has dropped its own rate (ogl.py:131-132,142)."""
+        return self.args.texture_lr * self.optimizer.param_groups[0]['lr'] / self.args.lr
+
+    def extra_optimizer(self, dataset):
+        lr = self._texture_lr()
+        if self._extra_optimizer is None:
+            return TextureOptimizerClass([{'params': self.textures[ds.id].parameters()} for ds in dataset], lr=lr)
+        self._extra_optimizer.param_groups[0]['lr'] = lr
+        return self._extra_optimizer
 
     def get_net(self):
         return self.net

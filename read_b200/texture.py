@@ -12,8 +12,11 @@ from . import _lib as L
 
 
 class Texture(nn.Module):
+    """Interface of the reference's texture modules (READ/models/texture.py:6-11): a regulariser that defaults to zero and a
+    ``null_grad`` every concrete texture must provide (train.py calls it when a dataset is unloaded)."""
+
     def null_grad(self):
-        raise NotImplementedError()
+        raise NotImplementedError(f"{type(self).__name__} does not implement null_grad()")
 
     def reg_loss(self):
         return 0.
@@ -34,31 +37,34 @@ class _Gather(torch.autograd.Function):
         return ops.texture_to_channel_major(g_nd), None         # [1,C,N]
 
 
+_INITIALISERS = {'zeros': torch.zeros, 'rand': torch.rand}
+
+
 class PointTexture(Texture):
+    """Per-point descriptors.  Constructor contract of READ/models/texture.py:14-35: ``texture_`` is a float32 Parameter of shape
+    [1, num_channels, size] (channel-major, the checkpoint layout), filled by ``init_method`` ('zeros' | 'rand'), or taken from a
+    pickled ``{'texture': module}`` checkpoint; ``activation`` in {'none', 'sigmoid', 'tanh'} is applied to the samples."""
+
     def __init__(self, num_channels, size, activation='none', checkpoint=None, init_method='zeros', reg_weight=0.):
         super().__init__()
         assert isinstance(size, int), 'size must be int'
-        shape = 1, num_channels, size
         if checkpoint:
-            self.texture_ = torch.load(checkpoint, map_location='cpu')['texture'].texture_
+            descriptors = torch.load(checkpoint, map_location='cpu')['texture'].texture_
         else:
-            if init_method == 'rand':
-                texture = torch.rand(shape)
-            elif init_method == 'zeros':
-                texture = torch.zeros(shape)
-            else:
+            make = _INITIALISERS.get(init_method)
+            if make is None:
                 raise ValueError(init_method)
-            self.texture_ = nn.Parameter(texture.float())
-        self.activation = activation
-        self.reg_weight = reg_weight
-        self._shadow = None
-        self._shadow_key = None
+            descriptors = nn.Parameter(make((1, num_channels, size), dtype=torch.float32))
+        self.texture_ = descriptors
+        self.activation, self.reg_weight = activation, reg_weight
+        self._shadow = self._shadow_key = None          # point-major copy for the gather kernels, see point_major()
 
     def null_grad(self):
         self.texture_.grad = None
 
     def reg_loss(self):
-        return self.reg_weight * torch.mean(torch.pow(self.texture_, 2))
+        """L2 regulariser of texture.py:40-41: reg_weight * mean(texture^2)."""
+        return self.reg_weight * self.texture_.square().mean()
 
     def point_major(self):
         """[N,C] shadow of ``texture_`` on its device, refreshed whenever the parameter changes."""

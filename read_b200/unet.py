@@ -13,6 +13,8 @@ Training (autograd enabled) is routed through torch's own conv/batch-norm operat
 a LIBRARY path (cuDNN), kept so that the reference's train.py keeps working; it is not the product hot path
 (DESIGN.md "out of scope this round": conv backward kernels).
 """
+import threading
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -97,22 +99,55 @@ class UNet(nn.Module):
         self.conv_impl = 'auto'
         self.use_graph = True
         self._engines = {}
+        self._engine_lock = threading.Lock()
+
+    # engines hold CUDA graphs and the lock is not picklable: copies / pickles of the module start with an empty cache
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop('_engine_lock', None)
+        state.pop('_vt', None)
+        state['_engines'] = {}
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._engines = {}
+        self._engine_lock = threading.Lock()
 
     # ------------------------------------------------------------------ engine management
     def _weights_version(self):
-        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+        """Sum of the in-place version counters of every parameter and buffer: changes on load_state_dict, optimizer steps and
+        BatchNorm running-stat updates.  The tensor list is cached (909 entries; rebuilt when the module is moved / cast, which
+        re-creates the tensors)."""
+        vt = self.__dict__.get('_vt')
+        if vt is None:
+            vt = self.__dict__['_vt'] = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in vt)
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__.pop('_vt', None)
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self.__dict__.pop('_vt', None)
+        return super().load_state_dict(*a, **kw)
 
     def engine(self, B, H, W, device):
+        """The static-shape executor for this (batch, size, device, mode), rebuilt when the weights changed.  The cache dict is
+        mutated in place under a lock: nn.DataParallel replicas share it with the source module (they are shallow copies)."""
         key = (B, H, W, str(device), self.precision, self.conv_impl, self.use_graph)
         ver = self._weights_version()
-        ent = self._engines.get(key)
-        if ent is None or ent[0] != ver:
-            eng = UNetEngine(self.state_dict(), B, H, W, device, precision=self.precision, conv_impl=self.conv_impl,
-                             use_graph=self.use_graph, base=self.base, num_res=self.num_res)
-            self._engines = {k: v for k, v in self._engines.items() if v[0] == ver}   # drop stale engines
+        with self._engine_lock:
+            ent = self._engines.get(key)
+            if ent is not None and ent[0] == ver:
+                return ent[1]
+            for k in [k for k, v in self._engines.items() if v[0] != ver]:     # drop stale engines
+                del self._engines[k]
+            with torch.cuda.device(device):
+                eng = UNetEngine(self.state_dict(), B, H, W, device, precision=self.precision, conv_impl=self.conv_impl,
+                                 use_graph=self.use_graph, base=self.base, num_res=self.num_res)
             self._engines[key] = (ver, eng)
             return eng
-        return ent[1]
 
     # ------------------------------------------------------------------ forward
     def forward(self, *inputs, **kwargs):
@@ -120,7 +155,11 @@ class UNet(nn.Module):
         x = inputs[0]
         needs_autograd = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                                       or any(t.requires_grad for t in inputs[:4]))
-        if needs_autograd or self.training:
+        # nn.DataParallel replicas (the reference's legacy multi-GPU eval, train.py:138-139) get freshly broadcast parameter
+        # copies every call: an engine cached for them could not see weight updates, and concurrent CUDA-graph captures from the
+        # replica threads would collide - replicas evaluate through torch's operators (library path, like training).
+        # read_b200's own multi-GPU path is read_b200.dist (one process per GPU).
+        if needs_autograd or self.training or getattr(self, '_is_replica', False):
             return self._forward_torch(inputs)
         if not x.is_cuda:
             raise RuntimeError("read_b200.UNet: inference needs CUDA tensors on a B200 (no CPU fallback)")

@@ -18,16 +18,17 @@ from .unet import UNet
 
 class FrameRenderer:
     def __init__(self, xyz, net_state_dict, texture, viewport_size, supersampling=1, temporal_average=False,
-                 device=None, flip_vertical=False, n_levels=4):
+                 device=None, flip_vertical=False, n_levels=4, return_net_input=True):
         """xyz: [N,3] float32 (numpy / tensor); net_state_dict: UNet checkpoint ``state_dict``; texture: the
-        ``[1,8,N]`` descriptor tensor (``PointTexture.texture_``) or a ``PointTexture``; viewport_size: (W, H)."""
+        ``[1,8,N]`` descriptor tensor (``PointTexture.texture_``) or a ``PointTexture``; viewport_size: (W, H) of the output
+        frame.  ``supersampling`` / ``temporal_average``: the options of READ/gl/nn.py:76,100-103 (the pyramid is rendered at
+        ss x the viewport and reduced bilinearly; every level is averaged with the previous frame's input), served on the fused
+        path.  ``return_net_input=False`` skips materialising the reference's ``net_input`` list (4 small transposes)."""
         W, H = int(viewport_size[0]), int(viewport_size[1])
         factor = 16
         assert W % 16 == 0, f'set width {factor * (W // factor)}'          # READ/gl/nn.py:107-109
         assert H % 16 == 0, f'set height {factor * (H // factor)}'
-        if supersampling != 1 or temporal_average:
-            # the fused path renders at the net's resolution; the index-map path (NetAndTexture.forward) keeps both options
-            raise NotImplementedError("FrameRenderer: supersampling / temporal_average are served by NetAndTexture.forward")
+        assert int(supersampling) >= 1, 'supersampling must be a positive integer'
         L.require_device(None if device is None else torch.device(device).index)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.W, self.H, self.n_levels = W, H, n_levels
@@ -35,7 +36,8 @@ class FrameRenderer:
         xyz = torch.as_tensor(np.asarray(xyz, dtype=np.float32) if not torch.is_tensor(xyz) else xyz, dtype=torch.float32)
         self.xyz = xyz.contiguous().to(self.device)
         # scene load: spatially sorted device store (original ids travel with the points), see ops.SortedPoints
-        nested = L.load().read_raster_direct_mask(W, H, n_levels) == 1        # every level exactly half of the previous one
+        ss = int(supersampling)
+        nested = L.load().read_raster_direct_mask(W * ss, H * ss, n_levels) == 1   # every level exactly half of the previous one
         self.store = ops.SortedPoints(self.xyz) if nested else None
         net = UNet()
         net.load_state_dict(net_state_dict, strict=True)
@@ -46,10 +48,10 @@ class FrameRenderer:
             with torch.no_grad():
                 tex.texture_.copy_(t)
             texture = tex
-        self.model = NetAndTexture(net, {0: texture}, 1)
+        self.model = NetAndTexture(net, {0: texture}, ss, temporal_average=bool(temporal_average))
+        self.return_net_input = bool(return_net_input)
         self.model.load_textures(0)
         self.model.to(self.device).eval()
-        self._rgba = torch.empty((H, W, 4), dtype=torch.float32, device=self.device)
 
     @classmethod
     def from_checkpoints(cls, xyz, net_ckpt, texture_ckpt, viewport_size, **kw):
@@ -66,11 +68,15 @@ class FrameRenderer:
         return (proj @ np.linalg.inv(view)).astype(np.float32)
 
     def infer(self, proj_matrix, view_matrix):
-        """-> {'output': [H,W,4] f32 cuda tensor (RGB, alpha 1; flipped if ``flip_vertical``), 'net_input': None}."""
+        """-> {'output': [H,W,4] f32 cuda tensor (RGB, alpha 1; flipped if ``flip_vertical``), 'net_input': list of the four
+        [1,8,h,w] f32 net inputs (None with ``return_net_input=False``)} - the contract of ``OGL.infer`` (READ/gl/nn.py:113-129).
+        Both are fresh tensors: the caller may keep them across frames, as with the reference."""
         m = torch.from_numpy(self.total_matrix(proj_matrix, view_matrix).reshape(1, 4, 4)).to(self.device)
         with torch.no_grad():
-            out = self.model.render(self.store if self.store is not None else self.xyz, m, self.W, self.H,
-                                    n_levels=self.n_levels)                                   # [1,3,H,W] f32
+            res = self.model.render(self.store if self.store is not None else self.xyz, m, self.W, self.H,
+                                    n_levels=self.n_levels, return_input=self.return_net_input, clone_output=False)
+        out, net_input = res if self.return_net_input else (res, None)                       # out: [1,3,H,W] f32
+        rgba = torch.empty((self.H, self.W, 4), dtype=torch.float32, device=self.device)
         L.check(L.load().read_frame_to_rgba(out.data_ptr(), self.H, self.W, int(self.flip_vertical), 1.0,
-                                             self._rgba.data_ptr(), L.stream_ptr()))
-        return {'output': self._rgba, 'net_input': None}
+                                             rgba.data_ptr(), L.stream_ptr()))
+        return {'output': rgba, 'net_input': net_input}

@@ -39,6 +39,10 @@ def _worker(rank, world, port, xyz, M, w, h, ret):
         idx, dep = oracle.pcpr_forward(xyz[start:start + count], M, w, h)
         gidx = np.where(dep != 0, idx + start, 0).astype(np.float32)
         keys = torch.from_numpy(_pack(gidx, dep))
+        # the frame path's collective: view r's plane goes to rank r only (B == world views)
+        mine = torch.empty(keys[0].numel(), dtype=torch.int64)
+        rdist.reduce_scatter_min_(mine, keys.reshape(-1).clone())
+        ret[("rs", rank)] = mine.numpy().copy()
         rdist.allreduce_min_(keys)
         ret[rank] = keys.numpy().copy()
     finally:
@@ -58,3 +62,4 @@ def test_sharded_min_reduce_equals_sequential(oracle_mod):
     mp.spawn(_worker, args=(world, port, xyz, M, 48, 32, ret), nprocs=world, join=True)
     for r in range(world):
         np.testing.assert_array_equal(ret[r], want)
+        np.testing.assert_array_equal(ret[("rs", r)], want[r].reshape(-1))       # reduce-scatter: rank r holds view r

@@ -217,7 +217,7 @@ def test_full_size_properties_10m_points():
     assert 0.3 < cov <= 1.0, cov
 
 
-@pytest.mark.parametrize("dedup", [1, 0, 2])          # 1 = in-warp per-pixel reduction, 2 = neighbour filter, 0 = neither (default)
+@pytest.mark.parametrize("dedup", [3, 1, 0, 2])       # 3 = streaming kernel (default); round-1 kernel: 1 = in-warp per-pixel reduction, 2 = neighbour filter, 0 = neither
 @pytest.mark.parametrize("n,W,H,L,t,depth,cell", [(100_000, 256, 256, 4, 0, 40.0, 0.25), (300_000, 128, 64, 3, 4, 40.0, 0.5),
                                                     (4097, 64, 32, 2, 9, 60.0, 1.0), (1_000_000, 512, 512, 4, 3, 250.0, 0.25)])
 def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell):
@@ -231,6 +231,7 @@ def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell
     assert torch.equal(torch.sort(store.perm).values, torch.arange(n, device=d))           # a permutation
     assert torch.equal(store.pts4[:, :3], torch.from_numpy(xyz).to(d)[store.perm])
     try:
+        Lb.check(lib.read_set_option(b"raster_stream", 1 if dedup == 3 else 0))
         Lb.check(lib.read_set_option(b"raster_dedup", 1 if dedup == 1 else 0))
         Lb.check(lib.read_set_option(b"raster_nbr_filter", 1 if dedup == 2 else 0))
         pyr = ops.Pyramid(1, W, H, L, d)
@@ -238,8 +239,28 @@ def test_sorted_store_is_bit_exact(oracle_mod, dedup, n, W, H, L, t, depth, cell
         ops.raster_project_sorted(pyr, store, torch.from_numpy(M).to(d))
         ops.raster_derive(pyr)
     finally:
+        Lb.check(lib.read_set_option(b"raster_stream", 1))
         Lb.check(lib.read_set_option(b"raster_dedup", 0))
         Lb.check(lib.read_set_option(b"raster_nbr_filter", 0))
+    for l, (w, h) in enumerate(oracle_mod.level_sizes(W, H, L)):
+        gi, gd = ops.zbuf_resolve(pyr, l)
+        oi, od = oracle_mod.pcpr_forward(xyz, M, w, h)
+        np.testing.assert_array_equal(gi.cpu().numpy(), oi, err_msg=f"index level {l}")
+        np.testing.assert_array_equal(gd.cpu().numpy().view(np.uint32), od.view(np.uint32), err_msg=f"depth level {l}")
+
+
+@pytest.mark.parametrize("n,B", [(200_000, 3), (5000, 8), (1_000_001, 2)])
+def test_sorted_store_multi_view_single_pass(oracle_mod, n, B):
+    """read_raster_project_sorted_views: B views rasterised in ONE pass over the store (the multi-GPU frame path) equal the
+    oracle view by view; n not a multiple of the 1024-point chunk exercises the partial last bulk copy."""
+    W, H, L = 256, 128, 4
+    xyz, M = scene_and_cams(n, W, H, list(range(2, 2 + B)), depth=80.0)
+    d = dev()
+    store = ops.SortedPoints(torch.from_numpy(xyz).to(d))
+    pyr = ops.Pyramid(B, W, H, L, d)
+    pyr.clear()
+    ops.raster_project_sorted(pyr, store, torch.from_numpy(M).to(d))
+    ops.raster_derive(pyr)
     for l, (w, h) in enumerate(oracle_mod.level_sizes(W, H, L)):
         gi, gd = ops.zbuf_resolve(pyr, l)
         oi, od = oracle_mod.pcpr_forward(xyz, M, w, h)

@@ -106,7 +106,7 @@ def test_module_surface_matches_reference_fixture(synth_sd):
         with torch.no_grad():
             out, net_input = model(dict(inputs), return_input=True)
         assert tuple(out.shape) == (2, 3, 48, 80) and out.is_cuda and len(net_input) == L_
-        np.testing.assert_array_equal(net_input[0].cpu().numpy(), g["feat0"])
+        np.testing.assert_array_equal(net_input[0].cpu().numpy(), g["feat0"][-1:])       # the last item's input, as the reference returns
         assert float((out.cpu() - want).abs().max()) < tol
     # per-item loop (different texture ids in one batch) gives the same frames as the batched pass
     tex2 = PointTexture(8, g["texture"].shape[-1])
@@ -170,3 +170,104 @@ def test_frame_renderer_matches_ogl_infer_contract():
     assert torch.equal(rf.infer(proj[0], view[0])['output'], want.flip(0))
     with pytest.raises(AssertionError, match="set width 112"):
         FrameRenderer(xyz, sd, tex, (120, 64))
+
+
+def _small_scene(n=60_000, W=128, H=64, ss=1):
+    from read_b200 import synth
+    xyz = synth.street_scene(n, depth=60.0, seed=5)
+    sd = synth.synth_state_dict(synth.SEED)
+    tex = torch.rand((1, 8, n), generator=torch.Generator().manual_seed(2))
+    net = UNet()
+    net.load_state_dict(sd, strict=True)
+    t = PointTexture(8, n)
+    with torch.no_grad():
+        t.texture_.copy_(tex)
+    model = NetAndTexture(net, {0: t}, ss)
+    model.load_textures(0)
+    model.cuda().eval()
+    return xyz, model
+
+
+def _index_inputs(oracle_mod, xyz, W, H, pose):
+    """The reference's input dict (one 'uv' key per level) from the oracle's index maps of one view."""
+    from read_b200 import synth
+    proj, view = synth.camera_batch(W, H, [pose])
+    M, idx, _ = oracle_mod.render_pyramid(xyz, proj, view, W, H, 4)
+    d = {(f"uv_1d_p1_ds{l}" if l else "uv_1d_p1"): torch.from_numpy(idx[l]).cuda() for l in range(4)}
+    d["id"] = 0
+    return torch.from_numpy(M).cuda(), d
+
+
+@pytest.mark.parametrize("ss", [2, 3])
+def test_fused_supersampling_equals_index_map_path(oracle_mod, ss):
+    """NetAndTexture.ss > 1 (READ/models/compose.py:162-163, READ/gl/nn.py:100-101): pyramid rendered at ss x the viewport, every
+    level reduced with F.interpolate(scale_factor=1/ss, 'bilinear').  The fused path's staging kernel must equal torch's
+    interpolate on the index-map path (fp32 parity mode: same net, so the RGB agrees to fp32 rounding)."""
+    W, H = 128, 64
+    xyz, model = _small_scene(W=W, H=H, ss=ss)
+    model.net.precision = "fp32"
+    M, inputs = _index_inputs(oracle_mod, xyz, W * ss, H * ss, 3)
+    with torch.no_grad():
+        want, want_in = model(dict(inputs), return_input=True)
+        got, got_in = model.render(torch.from_numpy(xyz).cuda(), M, W, H, return_input=True)
+    assert tuple(got.shape) == (1, 3, H, W)
+    for a, b in zip(got_in, want_in):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a - b).abs().max()) < 1e-6
+    assert float((got - want).abs().max()) < TOL_FP32
+    model.net.precision = "bf16"
+    with torch.no_grad():
+        got16 = model.render(torch.from_numpy(xyz).cuda(), M, W, H)
+    assert float((got16 - want).abs().max()) < TOL_BF16
+
+
+def test_fused_temporal_average_equals_index_map_path(oracle_mod):
+    """temporal_average (compose.py:167-171): the net input of frame t is the mean of its features and frame t-1's (already
+    averaged) input.  Three consecutive poses through the fused path and through the index-map path."""
+    W, H = 128, 64
+    xyz, model = _small_scene(W=W, H=H)
+    model.net.precision = "fp32"
+    model.temporal_average = True
+    x = torch.from_numpy(xyz).cuda()
+    outs_f, outs_i = [], []
+    for pose in (1, 2, 3):
+        M, inputs = _index_inputs(oracle_mod, xyz, W, H, pose)
+        with torch.no_grad():
+            outs_f.append(model.render(x, M, W, H))
+            outs_i.append(model(dict(inputs)))
+    for a, b in zip(outs_f, outs_i):
+        assert float((a - b).abs().max()) < TOL_FP32
+    assert float((outs_f[2] - outs_f[1]).abs().max()) > 1e-5            # the frames do differ
+    # switching the option off drops the history
+    model.temporal_average = False
+    M, inputs = _index_inputs(oracle_mod, xyz, W, H, 3)
+    with torch.no_grad():
+        plain = model.render(x, M, W, H)
+        model.last_input = None
+        want = model(dict(inputs))
+    assert float((plain - want).abs().max()) < TOL_FP32
+
+
+def test_frame_renderer_options_and_net_input(oracle_mod):
+    """FrameRenderer(supersampling, temporal_average) == OGL(..., supersampling, temporal_average) of READ/gl/nn.py:76-129:
+    'net_input' is the list the model saw, 'output' a fresh [H,W,4] tensor per call."""
+    from read_b200 import synth
+    from read_b200.viewer import FrameRenderer
+    W, H, n = 128, 64, 40_000
+    xyz = synth.street_scene(n, depth=60.0, seed=5)
+    sd = synth.synth_state_dict(synth.SEED)
+    tex = torch.rand((1, 8, n), generator=torch.Generator().manual_seed(2))
+    proj, view = synth.camera_batch(W, H, [3, 4])
+    r = FrameRenderer(xyz, sd, tex, (W, H), supersampling=2, temporal_average=True)
+    assert r.model.ss == 2 and r.model.temporal_average is True
+    a = r.infer(proj[0], view[0])
+    b = r.infer(proj[1], view[1])
+    assert a['output'].data_ptr() != b['output'].data_ptr()
+    assert len(a['net_input']) == 4 and tuple(a['net_input'][0].shape) == (1, 8, H, W) and a['net_input'][0].dtype == torch.float32
+    assert tuple(a['net_input'][3].shape) == (1, 8, H // 8, W // 8)
+    # frame 0 has no history: equals the plain ss = 2 render
+    r2 = FrameRenderer(xyz, sd, tex, (W, H), supersampling=2, return_net_input=False)
+    c = r2.infer(proj[0], view[0])
+    assert c['net_input'] is None
+    assert torch.equal(c['output'], a['output'])
+    assert not torch.equal(r2.infer(proj[1], view[1])['output'], b['output'])       # frame 1 is blended with frame 0
