@@ -38,10 +38,11 @@ enum {
 int read_version(void);
 const char *read_last_error(void);
 /* Tuning options.  Results are bit-identical for every accepted setting; unknown names and out-of-range values are rejected.
- *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = query),
+ *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = auto), "raster_stream" (1),
  *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0)
- *   convs:      "tc_mt" (supertile width, 0 = auto / 1 / 2 / 4; read when a plan is created), "tc_role_rot" (1),
- *               "tc_pdl" (1: programmatic dependent launch between consecutive conv kernels)
+ *   convs:      read when a plan is created: "tc_mt" (supertile width 1 (default) / 2 / 4, 0 = auto-widen), "tc_merge_done" (1),
+ *               "tc_commit_late" (0), "tc_bpair" (0); read at launch: "tc_role_rot" (1), "tc_pdl" (1: programmatic dependent
+ *               launch between consecutive conv kernels)
  * The options are process-wide tuning state (plain ints): set them before creating plans / launching, not concurrently with
  * launches from other threads.  Diagnostic knobs that skip work and therefore corrupt the output ("tc_debug", "tcg_debug",
  * raster_mode 4 / 5) exist only in builds compiled with -DREAD_DIAG and are absent from the shipped library. */
@@ -245,6 +246,32 @@ int read_stage_net_inputs(const float *src, int B, int hs, int ws, int C, int fa
 
 int read_nchw_f32_to_nhwc(const float *in, int B, int C, int H, int W, int act_dtype, void *out, void *stream);
 int read_nhwc_to_nchw_f32(const void *in, int act_dtype, int B, int C, int H, int W, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Strip-parallel refinement net across GPUs: halo rows travel between neighbouring ranks through
+ * peer-mapped mailboxes (cudaMalloc + CUDA IPC), one kernel per exchange, no NCCL on the path (csrc/halo.cu).
+ * read_ipc_alloc: cudaMalloc `bytes` (zero-filled) and export its 64-byte IPC handle; read_ipc_open maps a peer's handle
+ * (another process on the same node) with lazy peer access.  read_epoch_bump increments the device-resident frame counter.
+ * read_halo_exchange: push `bytes` from src_up / src_dn into the neighbours' mailbox slots (peer pointers) and publish the
+ * current epoch in their flag words; then wait until both neighbours' epochs arrived in this rank's flags and copy this rank's
+ * mailbox slots into dst_top / dst_bot.  Null pointers = no neighbour on that side.  Asynchronous on `stream`. */
+typedef struct read_halo_desc {
+    const void *src_up, *src_dn;               /* local rows to send to the strip above / below */
+    void *peer_up_slot, *peer_dn_slot;         /* destination slots inside the neighbours' mailboxes */
+    void *peer_up_flag, *peer_dn_flag;         /* uint32 flag words inside the neighbours' mailboxes */
+    const void *slot_from_up, *slot_from_dn;   /* this rank's mailbox slots (written by the neighbours) */
+    const void *flag_from_up, *flag_from_dn;   /* this rank's flag words */
+    void *dst_top, *dst_bot;                   /* halo rows of the local tensor */
+    int64_t bytes;                             /* per direction, multiple of 16 */
+    const void *epoch;                         /* uint32 device word, see read_epoch_bump */
+    void *cta_counter;                         /* uint32 device word private to this exchange, zero-initialised */
+} read_halo_desc;
+int read_ipc_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle64);
+int read_ipc_open(const unsigned char *handle64, void **peer_ptr);
+int read_ipc_close(void *peer_ptr);
+int read_ipc_free(void *dev_ptr);
+int read_epoch_bump(uint32_t *epoch, void *stream);
+int read_halo_exchange(const read_halo_desc *d, void *stream);
 
 /* Counts kernels launched by this library since load (bench.py's gpu_launches claim). */
 int64_t read_launch_count(void);

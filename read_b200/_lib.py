@@ -44,6 +44,13 @@ class ReadConvDesc(ctypes.Structure):
     ]
 
 
+class ReadHaloDesc(ctypes.Structure):
+    _fields_ = [("src_up", c_vp), ("src_dn", c_vp), ("peer_up_slot", c_vp), ("peer_dn_slot", c_vp),
+                ("peer_up_flag", c_vp), ("peer_dn_flag", c_vp), ("slot_from_up", c_vp), ("slot_from_dn", c_vp),
+                ("flag_from_up", c_vp), ("flag_from_dn", c_vp), ("dst_top", c_vp), ("dst_bot", c_vp),
+                ("bytes", c_i64), ("epoch", c_vp), ("cta_counter", c_vp)]
+
+
 _SIGS = {
     "read_version": (c_int, []),
     "read_last_error": (ctypes.c_char_p, []),
@@ -58,6 +65,12 @@ _SIGS = {
     "read_raster_derive_levels": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_sorted": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_sorted_views": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_ipc_alloc": (c_int, [c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    "read_ipc_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "read_ipc_close": (c_int, [c_vp]),
+    "read_ipc_free": (c_int, [c_vp]),
+    "read_epoch_bump": (c_int, [c_vp, c_vp]),
+    "read_halo_exchange": (c_int, [ctypes.POINTER(ReadHaloDesc), c_vp]),
     "read_stage_net_inputs": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]),
     "read_raster_direct_mask": (c_u32, [c_int, c_int, c_int]),
     "read_zbuf_resolve": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -791,8 +791,11 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
 struct TcGeom {
     int cin_blk, kchunks, n_tile, n_tiles, cout_pad;
 };
-int g_tc_commit_late = 0, g_tc_merge_done = 0, g_tc_bpair = 0;     // experiments (read_set_option), read at plan creation
-int g_tc_mt = 0;          // supertile width override (read_set_option "tc_mt"): 0 = auto, 1 / 2 / 4 = force where legal
+// Issue-side tuning, read at plan creation (read_set_option).  Measured ABAB on the C3 layers (profiles/r02_conv_experiments.md):
+//   tc_merge_done 1: ONE tcgen05.commit per tile for resident-weight, single-K-chunk layers (C=32: 87 -> 79 us, 97 -> 87 us)
+//   tc_commit_late / tc_bpair: fewer commits for supertiles / streamed weights - no gain, off
+int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0;
+int g_tc_mt = 1;          // supertile width (read_set_option "tc_mt"): 1 = plain 8x16 tiles (default: measured fastest), 0 = auto-widen, 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
 static int desc_chan_gran(const read_conv_desc &d)
 {

@@ -151,6 +151,30 @@ __device__ __forceinline__ void store_desc8<float>(float *out, long long pix, co
     o[1] = __ldg(t + 1);
 }
 
+__device__ __forceinline__ void load_desc8(const float *tex, long long N, unsigned long long key, float4 (&d)[2])
+{
+    long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
+    if (id >= N) id = N - 1;
+    const float4 *t = reinterpret_cast<const float4 *>(tex + id * 8);
+    d[0] = __ldg(t);
+    d[1] = __ldg(t + 1);
+}
+template <typename TO> __device__ __forceinline__ void write_desc8(TO *out, long long pix, const float4 (&d)[2]);
+template <> __device__ __forceinline__ void write_desc8<__nv_bfloat16>(__nv_bfloat16 *out, long long pix, const float4 (&d)[2])
+{
+    __nv_bfloat162 r[4] = {__floats2bfloat162_rn(d[0].x, d[0].y), __floats2bfloat162_rn(d[0].z, d[0].w),
+                           __floats2bfloat162_rn(d[1].x, d[1].y), __floats2bfloat162_rn(d[1].z, d[1].w)};
+    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(r);
+}
+template <> __device__ __forceinline__ void write_desc8<float>(float *out, long long pix, const float4 (&d)[2])
+{
+    float4 *o = reinterpret_cast<float4 *>(out + pix * 8);
+    o[0] = d[0];
+    o[1] = d[1];
+}
+
+int g_gather_variant = 0;     // read_set_option("gather_variant"): 0 = gathers next to their stores, 1 / 2 = all gathers hoisted (64 regs / free)
+
 struct FusedArgs {
     const float *tex;
     long long N;
@@ -166,8 +190,8 @@ __device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, i
     return (unsigned long long)__shfl_xor_sync(0xffffffffu, (long long)v, m);
 }
 
-template <typename TO>
-__global__ void __launch_bounds__(256) pyramid_resolve_gather_kernel(const __grid_constant__ FusedArgs a)
+template <typename TO, int V>
+__global__ void __launch_bounds__(256, V == 1 ? 4 : 1) pyramid_resolve_gather_kernel(const __grid_constant__ FusedArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int bw = a.W >> 3, bh = a.H >> 3;
@@ -184,9 +208,6 @@ __global__ void __launch_bounds__(256) pyramid_resolve_gather_kernel(const __gri
         unsigned long long *zp = a.z[0] + p0;
         const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(zp);            // x is even, level base is 16B aligned
         if (a.reset0) *reinterpret_cast<ulonglong2 *>(zp) = make_ulonglong2(ZBUF_EMPTY, ZBUF_EMPTY);
-        TO *o0 = static_cast<TO *>(a.out[0]);
-        store_desc8<TO>(o0, p0, a.tex, a.N, k.x);
-        store_desc8<TO>(o0, p0 + 1, a.tex, a.N, k.y);
         // level 1: 2x2 min = horizontal pair (in-lane) + vertical pair (lane ^ 4)
         unsigned long long m1 = umin64(k.x, k.y);
         m1 = umin64(m1, shfl_xor64(m1, 4));
@@ -196,23 +217,58 @@ __global__ void __launch_bounds__(256) pyramid_resolve_gather_kernel(const __gri
         // level 3: horizontal lane ^ 2, vertical lane ^ 16
         unsigned long long m3 = umin64(m2, shfl_xor64(m2, 2));
         m3 = umin64(m3, shfl_xor64(m3, 16));
-        if ((row & 1) == 0) {
-            const int W1 = a.W >> 1, H1 = a.H >> 1;
-            const long long p1 = ((long long)b * H1 + (y >> 1)) * W1 + (x >> 1);
-            a.z[1][p1] = m1;
-            store_desc8<TO>(static_cast<TO *>(a.out[1]), p1, a.tex, a.N, m1);
-            if ((row & 2) == 0 && (lane & 1) == 0) {
-                const int W2 = a.W >> 2, H2 = a.H >> 2;
-                const long long p2 = ((long long)b * H2 + (y >> 2)) * W2 + (x >> 2);
-                a.z[2][p2] = m2;
-                store_desc8<TO>(static_cast<TO *>(a.out[2]), p2, a.tex, a.N, m2);
-                if (lane == 0) {
-                    const int W3 = a.W >> 3, H3 = a.H >> 3;
-                    const long long p3 = ((long long)b * H3 + (y >> 3)) * W3 + (x >> 3);
-                    a.z[3][p3] = m3;
-                    store_desc8<TO>(static_cast<TO *>(a.out[3]), p3, a.tex, a.N, m3);
-                }
+        // ALL descriptor reads of the block are issued before the first store (round-2 ncu: 14.5 warps stalled on long
+        // scoreboard per issue - the level-1..3 gathers used to wait behind the level-0 stores, up to five serial DRAM round
+        // trips per block; now it is two: keys, then descriptors)
+        const bool p1 = (row & 1) == 0, p2 = p1 && (row & 2) == 0 && (lane & 1) == 0, p3 = lane == 0;
+        if (V == 0) {           // round-1 order: every gather next to its store
+            TO *o0 = static_cast<TO *>(a.out[0]);
+            float4 d[2];
+            load_desc8(a.tex, a.N, k.x, d); write_desc8<TO>(o0, p0, d);
+            load_desc8(a.tex, a.N, k.y, d); write_desc8<TO>(o0, p0 + 1, d);
+            if (p1) {
+                const long long p1i = ((long long)b * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1);
+                a.z[1][p1i] = m1;
+                load_desc8(a.tex, a.N, m1, d); write_desc8<TO>(static_cast<TO *>(a.out[1]), p1i, d);
             }
+            if (p2) {
+                const long long p2i = ((long long)b * (a.H >> 2) + (y >> 2)) * (a.W >> 2) + (x >> 2);
+                a.z[2][p2i] = m2;
+                load_desc8(a.tex, a.N, m2, d); write_desc8<TO>(static_cast<TO *>(a.out[2]), p2i, d);
+            }
+            if (p3) {
+                const long long p3i = ((long long)b * (a.H >> 3) + (y >> 3)) * (a.W >> 3) + (x >> 3);
+                a.z[3][p3i] = m3;
+                load_desc8(a.tex, a.N, m3, d); write_desc8<TO>(static_cast<TO *>(a.out[3]), p3i, d);
+            }
+            continue;
+        }
+        float4 d0[2], d1[2], d2[2], d3[2], d4[2];
+        load_desc8(a.tex, a.N, k.x, d0);
+        load_desc8(a.tex, a.N, k.y, d1);
+        if (p1) load_desc8(a.tex, a.N, m1, d2);
+        if (p2) load_desc8(a.tex, a.N, m2, d3);
+        if (p3) load_desc8(a.tex, a.N, m3, d4);
+        TO *o0 = static_cast<TO *>(a.out[0]);
+        write_desc8<TO>(o0, p0, d0);
+        write_desc8<TO>(o0, p0 + 1, d1);
+        if (p1) {
+            const int W1 = a.W >> 1, H1 = a.H >> 1;
+            const long long p1i = ((long long)b * H1 + (y >> 1)) * W1 + (x >> 1);
+            a.z[1][p1i] = m1;
+            write_desc8<TO>(static_cast<TO *>(a.out[1]), p1i, d2);
+        }
+        if (p2) {
+            const int W2 = a.W >> 2, H2 = a.H >> 2;
+            const long long p2i = ((long long)b * H2 + (y >> 2)) * W2 + (x >> 2);
+            a.z[2][p2i] = m2;
+            write_desc8<TO>(static_cast<TO *>(a.out[2]), p2i, d3);
+        }
+        if (p3) {
+            const int W3 = a.W >> 3, H3 = a.H >> 3;
+            const long long p3i = ((long long)b * H3 + (y >> 3)) * W3 + (x >> 3);
+            a.z[3][p3i] = m3;
+            write_desc8<TO>(static_cast<TO *>(a.out[3]), p3i, d4);
         }
     }
 }
@@ -363,10 +419,13 @@ int read_pyramid_resolve_gather(const float *tex_nd, int D, int64_t N, uint64_t 
     long long ctas = (nblocks + 7) / 8;
     const long long cap = (long long)num_sms() * 16;
     if (ctas > cap) ctas = cap;
-    if (layout == READ_FEAT_NHWC_BF16)
-        pyramid_resolve_gather_kernel<__nv_bfloat16><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a);
-    else
-        pyramid_resolve_gather_kernel<float><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a);
+    const int v = g_gather_variant;
+#define RB_PRG(T_) do { if (v == 1) pyramid_resolve_gather_kernel<T_, 1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
+                        else if (v == 2) pyramid_resolve_gather_kernel<T_, 2><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
+                        else pyramid_resolve_gather_kernel<T_, 0><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); } while (0)
+    if (layout == READ_FEAT_NHWC_BF16) RB_PRG(__nv_bfloat16);
+    else RB_PRG(float);
+#undef RB_PRG
     RB_LAUNCH_CHECK();
     return READ_OK;
 }

@@ -75,3 +75,35 @@ def render_sharded(pyr, xyz_shard, id_base, total_m, group=None):
     allreduce_min_(pyr.buf[lo:hi], group)
     ops.raster_derive(pyr)
     return pyr
+
+
+class StripFrameRenderer:
+    """Latency mode: ``world`` GPUs cooperate on ONE frame.  Rank r rasterises its spatial tile of the
+    scene, ONE all-reduce(min) makes the packed level-0 z-buffer complete on every rank, every rank gathers the feature pyramid
+    and refines its horizontal strip with ``engine.StripEngine`` (halo rows exchanged layer by layer over NVLink peer memory);
+    the strips are all-gathered into the full frame on every rank."""
+
+    def __init__(self, store_shard, texture_point_major, state_dict, W, H, device, group=None):
+        from . import ops, _lib as L
+        from .engine import StripEngine
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.group, self.W, self.H, self.device = group, W, H, device
+        self.store, self.tex = store_shard, texture_point_major
+        self.pyr = ops.Pyramid(1, W, H, 4, device)
+        self.eng = StripEngine(state_dict, H, W, device, self.rank, self.world, group=group)
+        self.full_feats = [torch.empty((1, H >> l, W >> l, 8), dtype=torch.bfloat16, device=device) for l in range(4)]
+        self.strips_out = torch.empty((self.world, 3, H // self.world, W), dtype=torch.float32, device=device)
+        self._ops, self._L = ops, L
+
+    def render(self, total_m):
+        """total_m [1,4,4] cuda f32 (the same on every rank) -> [3,H,W] f32 frame, identical on every rank."""
+        ops, L = self._ops, self._L
+        pyr, plane = self.pyr, self.W * self.H
+        L.check(L.load().read_zbuf_clear(pyr.buf.data_ptr(), plane, L.stream_ptr()))
+        ops.raster_project_sorted(pyr, self.store, total_m)
+        allreduce_min_(pyr.buf[:plane], self.group)
+        ops.pyramid_resolve_gather(self.tex, pyr, self.full_feats, L.FEAT_NHWC_BF16)
+        self.eng.set_inputs_from_full(self.full_feats)
+        self.eng.run()
+        dist.all_gather_into_tensor(self.strips_out, self.eng.output_interior[0].contiguous(), group=self.group)
+        return self.strips_out.permute(1, 0, 2, 3).reshape(3, self.H, self.W)

@@ -15,7 +15,7 @@ _MODE = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_U
 
 
 class _Layer:
-    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride")
+    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride", "kind")
 
 
 class UNetEngine:
@@ -68,6 +68,7 @@ class UNetEngine:
         ``cin_slice`` = (c0, c1): this launch covers input channels [c0, c1) of the layer's weights (one term of a 1x1 conv
         over a multi-resolution concat, see ``_aff``)."""
         lib = self.lib
+        self._before_conv(srcs, k, stride, residual, out2_mul, addin)
         d = L.ReadConvDesc()
         d.act_dtype = self.act_code
         d.n_src = len(srcs)
@@ -154,10 +155,18 @@ class UNetEngine:
         ly = _Layer()
         ly.name, ly.plan, ly.impl, ly.keep = (name or prefix), plan, lib.read_conv_plan_impl(plan), keep
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
-        ly.k, ly.stride = k, stride
+        ly.k, ly.stride, ly.kind = k, stride, "conv"
         self.layers.append(ly)
         self.ops.append(ly)
+        self._after_conv(srcs, k, stride, out, out2, residual, out2_mul, addin, final)
         return (out, out2) if out2_mul is not None else out
+
+    # hooks of the strip-parallel engine (StripEngine): halo validity tracking around every conv; no-ops here
+    def _before_conv(self, srcs, k, stride, residual, out2_mul, addin):
+        pass
+
+    def _after_conv(self, srcs, k, stride, out, out2, residual, out2_mul, addin, final):
+        pass
 
     def _merge_src(self, t):
         """Decoder skip merge input: nn.Upsample(x4, bilinear) of ``t`` (unet.py:260,268,276).  In bf16 mode the upsample is a
@@ -168,7 +177,7 @@ class UNetEngine:
         B, h, w, c = t.shape
         out = torch.empty((B, 4 * h, 4 * w, c), dtype=self.adt, device=self.device)
         op = _Layer()
-        op.name, op.plan, op.impl, op.flops, op.k, op.stride = f"upsample4({h}x{w}x{c})", None, -1, 0, 0, 0
+        op.name, op.plan, op.impl, op.flops, op.k, op.stride, op.kind = f"upsample4({h}x{w}x{c})", None, -1, 0, 0, 0, "upsample"
         op.keep = [t, out, (t.data_ptr(), B, h, w, c, out.data_ptr())]
         self.ops.append(op)
         return (out, "id", 1)
@@ -224,10 +233,18 @@ class UNetEngine:
         return self._conv(f"AFFs.{idx}.conv.1", [(a, "id", 1)], c, 3, 1, False)
 
     def _build(self):
-        B, H, W, c = self.B, self.H, self.W, self.base
-        dev, adt = self.device, self.adt
-        self.inputs = [torch.zeros((B, H >> l, W >> l, 8), dtype=adt, device=dev) for l in range(4)]
-        x, x2, x4, x8 = self.inputs
+        self.inputs = self._make_inputs()
+        self.output = self._build_graph(self.inputs)
+        self.flops = sum(l.flops for l in self.layers)
+        torch.cuda.current_stream().synchronize()   # weight packing done before any capture
+
+    def _make_inputs(self):
+        return [torch.zeros((self.B, self.H >> l, self.W >> l, 8), dtype=self.adt, device=self.device) for l in range(4)]
+
+    def _build_graph(self, inputs):
+        """UNet.forward (READ/models/unet.py:202-285) as a sequence of fused gated-conv launches; returns the output tensor."""
+        c = self.base
+        x, x2, x4, x8 = inputs
         z2 = self._scm("SCM2", x2, 2 * c)
         z4 = self._scm("SCM1", x4, 4 * c)
         z8 = self._scm("SCM0", x8, 8 * c)
@@ -253,9 +270,7 @@ class UNetEngine:
         t = self._conv("feat_extract.4", [(z, "id", 1)], c, 4, 2, True)
         z = self._conv("Convs.2", [self._merge_src(t), (r1, "id", 1)], c, 1, 1, True)
         z = self._block("Decoder.3", z, c)
-        self.output = self._conv("feat_extract.5", [(z, "id", 1)], 3, 3, 1, False, final=True)
-        self.flops = sum(l.flops for l in self.layers)
-        torch.cuda.current_stream().synchronize()   # weight packing done before any capture
+        return self._conv("feat_extract.5", [(z, "id", 1)], 3, 3, 1, False, final=True)
 
     # ------------------------------------------------------------------ execution
     def _launch_all(self):
@@ -267,9 +282,14 @@ class UNetEngine:
         stream = L.stream_ptr() if stream is None else stream
         if op.plan is not None:
             L.check(self.lib.read_conv_plan_launch(op.plan, stream))
-        else:
+        elif op.kind == "upsample":
             src, B, h, w, c, dst = op.keep[2]
             L.check(self.lib.read_upsample_bilinear4(src, self.act_code, B, h, w, c, dst, stream))
+        else:
+            self._launch_aux(op, stream)
+
+    def _launch_aux(self, op, stream):
+        raise RuntimeError(f"unknown engine op {op.kind}")
 
     def run(self):
         """Run the net on whatever is in ``self.inputs``; result in ``self.output`` ([B,3,H,W] f32)."""
@@ -310,6 +330,196 @@ class UNetEngine:
     def __del__(self):
         try:
             for ly in self.layers:
-                self.lib.read_conv_plan_destroy(ly.plan)
+                if ly.plan is not None:
+                    self.lib.read_conv_plan_destroy(ly.plan)
         except Exception:
             pass
+
+
+class StripEngine(UNetEngine):
+    """Strip-parallel refinement net: rank ``rank`` of ``world`` GPUs refines rows
+    [rank * H / world, (rank + 1) * H / world) of ONE frame; see ``read_b200.strips`` for the halo bookkeeping and
+    ``csrc/halo.cu`` for the exchange kernel (peer-mapped mailboxes over NVLink, no NCCL between the layers).
+
+    ``self.inputs`` are the local crops (with halos) of the feature pyramid - fill them with ``set_inputs_from_full``;
+    ``self.output_interior`` is this rank's [1,3,S,W] slice of the frame.  All ranks must call ``run()`` together."""
+
+    def __init__(self, state_dict, H, W, device, rank, world, group=None, precision="bf16", use_graph=True):
+        from . import strips
+        assert precision == "bf16", "the strip engine runs the production (tcgen05) path"
+        self.rank, self.world, self.group = rank, world, group
+        self.H_full = H
+        _, H_local, self.h_top, self.h_bot = strips.strip_rows(H, world, rank, 0)
+        self.S = H // world
+        self._strips = strips
+        self._meta = {}           # id(tensor) -> [level, valid halo rows]
+        self._exch = []           # [(tensor, level)] in op order
+        super().__init__(state_dict, 1, H_local, W, device, precision=precision, conv_impl="auto", use_graph=use_graph)
+        self._setup_mailbox()
+
+    # ------------------------------------------------------------------ halo bookkeeping (build time)
+    def _level_of(self, rows):
+        l = 0
+        while (self.H >> l) != rows:
+            l += 1
+            assert l <= 4, (rows, self.H)
+        return l
+
+    def _v(self, t):
+        m = self._meta.get(id(t))
+        if m is None:             # an engine input: a crop of true data, halo fully valid
+            m = self._meta[id(t)] = [self._level_of(t.shape[1]), self._strips.halo_rows(self._level_of(t.shape[1]))]
+        return m
+
+    def _exchange(self, t):
+        m = self._v(t)
+        op = _Layer()
+        op.name, op.plan, op.impl, op.flops, op.k, op.stride, op.kind = f"halo(l{m[0]}, {t.shape[3]}ch)", None, -1, 0, 0, 0, "halo"
+        op.keep = [t, len(self._exch)]
+        self._exch.append((t, m[0]))
+        self.ops.append(op)
+        m[1] = self._strips.halo_rows(m[0])
+
+    def _before_conv(self, srcs, k, stride, residual, out2_mul, addin):
+        if self.world == 1:
+            return
+        st = self._strips
+        need = st.conv_need(k)
+        for (t, mode, f) in srcs:
+            m = self._v(t)
+            l_in = m[0] if mode == "id" else (m[0] + {2: 1, 4: 2, 8: 3}[f] if mode == "down" else
+                                              m[0] - ({2: 1, 4: 2, 8: 3}[f] if mode == "up" else 2))
+            if st.src_validity(m[1], mode, f, st.halo_rows(l_in)) < need:
+                self._exchange(t)
+                assert st.src_validity(m[1], mode, f, st.halo_rows(l_in)) >= need
+
+    def _after_conv(self, srcs, k, stride, out, out2, residual, out2_mul, addin, final):
+        if self.world == 1:
+            return
+        st = self._strips
+        v_in, l_in = None, None
+        for (t, mode, f) in srcs:
+            m = self._v(t)
+            l_in = m[0] if mode == "id" else (m[0] + {2: 1, 4: 2, 8: 3}[f] if mode == "down" else
+                                              m[0] - ({2: 1, 4: 2, 8: 3}[f] if mode == "up" else 2))
+            ve = st.src_validity(m[1], mode, f, st.halo_rows(l_in))
+            v_in = ve if v_in is None else min(v_in, ve)
+        l_out = l_in + (1 if stride == 2 else 0)
+        v = min(st.conv_out_validity(v_in, k, stride), st.halo_rows(l_out))
+        if residual is not None:
+            v = min(v, self._v(residual)[1])
+        if addin is not None:                       # RAW tensor of the next-coarser level, nearest x2
+            v = min(v, 2 * self._v(addin)[1])
+        self._meta[id(out)] = [l_out, v]
+        if out2 is not None:
+            self._meta[id(out2)] = [l_out, min(v, self._v(out2_mul)[1])]
+
+    def _merge_src(self, t):
+        # bilinear x4 reads one source row beyond the strip for its first / last interior rows
+        if self.world > 1 and self._v(t)[1] < 1:
+            self._exchange(t)
+        src = super()._merge_src(t)
+        if self.world > 1 and src[1] == "id":       # the separate bilinear-x4 kernel wrote a new tensor
+            m = self._v(t)
+            self._meta[id(src[0])] = [m[0] - 2, self._strips.src_validity(m[1], "bil4", 4, self._strips.halo_rows(m[0] - 2))]
+        return src
+
+    def _build(self):
+        if self.world > 1:
+            op = _Layer()
+            op.name, op.plan, op.impl, op.flops, op.k, op.stride, op.kind, op.keep = "epoch", None, -1, 0, 0, 0, "epoch", []
+            self.ops.append(op)
+        super()._build()
+        self.output_interior = self.output[:, :, self.h_top:self.h_top + self.S]
+
+    # ------------------------------------------------------------------ mailboxes (after the op list is known)
+    def _setup_mailbox(self):
+        import torch.distributed as dist
+        self._mail = None
+        if self.world == 1:
+            return
+        assert len(self._exch) >= 2, "the mailbox protocol needs at least two exchanges per frame (csrc/halo.cu)"
+        lib = self.lib
+        n = len(self._exch)
+        esize = 2
+        # layout (identical on every rank): [flags: n x 2 u32][counters: n u32][epoch u32] padded to 1 KB, then per exchange two slots
+        head = ((n * 2 + n + 1) * 4 + 1023) // 1024 * 1024
+        offs, o = [], head
+        for (t, lvl) in self._exch:
+            nbytes = self._strips.halo_rows(lvl) * t.shape[2] * t.shape[3] * esize
+            assert nbytes % 16 == 0
+            offs.append((o, o + ((nbytes + 255) // 256 * 256), nbytes))
+            o += 2 * ((nbytes + 255) // 256 * 256)
+        ptr = L.c_vp()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            L.check(lib.read_ipc_alloc(o, ctypes.byref(ptr), handle))
+        self._mail = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        self._peers = {}
+        for nb in (self.rank - 1, self.rank + 1):
+            if 0 <= nb < self.world:
+                pp = L.c_vp()
+                with torch.cuda.device(self.device):
+                    L.check(lib.read_ipc_open(handles[nb], ctypes.byref(pp)))
+                self._peers[nb] = pp.value
+        up, dn = self._peers.get(self.rank - 1), self._peers.get(self.rank + 1)
+        self._epoch_ptr = self._mail + (n * 3) * 4
+        self._descs = []
+        for e, (t, lvl) in enumerate(self._exch):
+            h = self._strips.halo_rows(lvl)
+            row = t.shape[2] * t.shape[3] * esize
+            Hl = t.shape[1]
+            ht = h if self.rank > 0 else 0
+            hb = h if self.rank < self.world - 1 else 0
+            slot_up, slot_dn, nbytes = offs[e]           # slot written by the upper / the lower neighbour
+            d = L.ReadHaloDesc()
+            base = t.data_ptr()
+            if up is not None:
+                d.src_up = base + ht * row                               # my first interior rows -> the upper rank's "from below" slot
+                d.peer_up_slot = up + slot_dn
+                d.peer_up_flag = up + (e * 2 + 1) * 4
+                d.slot_from_up = self._mail + slot_up
+                d.flag_from_up = self._mail + (e * 2 + 0) * 4
+                d.dst_top = base
+            if dn is not None:
+                d.src_dn = base + (Hl - hb - h) * row                    # my last interior rows -> the lower rank's "from above" slot
+                d.peer_dn_slot = dn + slot_up
+                d.peer_dn_flag = dn + (e * 2 + 0) * 4
+                d.slot_from_dn = self._mail + slot_dn
+                d.flag_from_dn = self._mail + (e * 2 + 1) * 4
+                d.dst_bot = base + (Hl - hb) * row
+            d.bytes = nbytes
+            d.epoch = self._epoch_ptr
+            d.cta_counter = self._mail + (n * 2 + e) * 4
+            self._descs.append(d)
+        dist.barrier(group=self.group)                # every mailbox is mapped before anyone pushes
+
+    def _launch_aux(self, op, stream):
+        if op.kind == "epoch":
+            L.check(self.lib.read_epoch_bump(self._epoch_ptr, stream))
+        elif op.kind == "halo":
+            L.check(self.lib.read_halo_exchange(ctypes.byref(self._descs[op.keep[1]]), stream))
+        else:
+            raise RuntimeError(f"unknown engine op {op.kind}")
+
+    def n_exchanges(self):
+        return len(self._exch)
+
+    def set_inputs_from_full(self, full_feats):
+        """full_feats[l]: [1, H >> l, W >> l, 8] in the engine's activation dtype (the whole frame's feature pyramid) -> copy
+        this rank's crop (strip + halos) of every level into the engine inputs."""
+        for l in range(4):
+            a, n, _, _ = self._strips.strip_rows(self.H_full, self.world, self.rank, l)
+            self.inputs[l].copy_(full_feats[l][:, a:a + n])
+
+    def __del__(self):
+        try:
+            for p in getattr(self, "_peers", {}).values():
+                self.lib.read_ipc_close(p)
+            if getattr(self, "_mail", None):
+                self.lib.read_ipc_free(self._mail)
+        except Exception:
+            pass
+        super().__del__()

@@ -25,8 +25,8 @@ def setopt(**kw):
 refs = []
 for m in mats:
     pyr.clear(); ops.raster_project(pyr, x0, m); torch.cuda.synchronize(); refs.append(pyr.buf.clone())
-variants = [("legacy", dict(raster_stream=0, raster_occupancy=0)), ("stream occ=auto", dict(raster_stream=1, raster_occupancy=0)),
-            ("stream occ=2", dict(raster_stream=1, raster_occupancy=2)), ("stream occ=1", dict(raster_stream=1, raster_occupancy=1))]
+variants = [("legacy", dict(raster_stream=0, raster_occupancy=0)), ("stream 4 CTA/SM", dict(raster_stream=1, raster_occupancy=4)),
+            ("stream 3 CTA/SM", dict(raster_stream=1, raster_occupancy=0)), ("stream 2 CTA/SM", dict(raster_stream=1, raster_occupancy=2))]
 times = {k: [] for k, _ in variants}
 bad = {k: 0 for k, _ in variants}
 for k, o in variants:
@@ -50,3 +50,21 @@ for k, _ in variants:
     print(f"{k:18s}: median {med:7.1f} us  best {ts[0]:7.1f} us  {16 * N / (med * 1e-6) / 1e9:7.1f} GB/s of the 16 B/point store  mismatching keys {bad[k]}")
 if len(sys.argv) > 1:
     json.dump(rows, open(sys.argv[1], "w"), indent=1)
+
+# resolve + gather (fused) on the state the rasterizer leaves
+tex = torch.rand((N, 8), device=dev)
+pyr4 = ops.Pyramid(1, W, H, 4, dev)
+outs = [torch.empty((1, H >> l, W >> l, 8), dtype=torch.bfloat16, device=dev) for l in range(4)]
+pyr4.clear()
+gts = {0: [], 1: [], 2: []}
+for rep in range(10):
+    for v in (0, 1, 2):
+        setopt(gather_variant=v)
+        ops.raster_project_sorted(pyr4, store, mats[0]); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.pyramid_resolve_gather(tex, pyr4, outs, L.FEAT_NHWC_BF16, reset_level0=True); b.record(); torch.cuda.synchronize()
+        gts[v].append(a.elapsed_time(b) * 1e3)
+setopt(gather_variant=0)
+for v in (0, 1, 2):
+    ts = sorted(gts[v][2:])
+    print(f"pyramid_resolve_gather variant {v}: median {ts[len(ts)//2]:6.1f} us  best {ts[0]:6.1f} us")
