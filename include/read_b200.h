@@ -273,6 +273,31 @@ int read_ipc_free(void *dev_ptr);
 int read_epoch_bump(uint32_t *epoch, void *stream);
 int read_halo_exchange(const read_halo_desc *d, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Descriptor side of the training step (replaces autograd's dense index_add_ of READ/models/texture.py:55-63
+ * and the dense torch.optim.RMSprop of READ/pipelines/ogl.py:16,97-102).  grad_nd [N,D] f32 and touched [N] u8 are persistent,
+ * zero-initialised accumulators owned by the caller.
+ *   read_gather_backward_sparse : grad_nd[id,:] += grad_out[b,:,y,x] for every pixel (ids [B,h,w] f32, grad_out [B,D,h,w] f32);
+ *                                 touched[id] = 1
+ *   read_sparse_rmsprop_step    : for touched points only - square_avg (point-major [N,D]) decayed lazily by alpha^(step -
+ *                                 last_step[i]), RMSprop update (momentum 0, not centered) applied to param_cn ([1,D,N], the
+ *                                 checkpoint layout) AND to shadow_nd ([N,D], may be null); the point's grad row and flag are
+ *                                 cleared.  step counts optimizer steps from 1.
+ *   read_square_avg_dense       : the dense optimizer's square_avg [1,D,N] after `step` steps (state_dict export)
+ *   read_compact_touched        : touched rows -> (id, grad[D]) pairs; *count (zeroed by the caller) receives their number
+ *   read_scatter_pairs          : grad_nd[id,:] += grads[k,:], touched[id] = 1 (pairs received from other ranks) */
+int read_gather_backward_sparse(const float *grad_out, const float *ids, int B, int D, int h, int w, int64_t N,
+                                float *grad_nd, unsigned char *touched, void *stream);
+int read_sparse_rmsprop_step(float *param_cn, float *shadow_nd, float *grad_nd, unsigned char *touched, float *square_avg,
+                             int32_t *last_step, int64_t N, int D, int step, float lr, float alpha, float eps, float weight_decay,
+                             void *stream);
+int read_square_avg_dense(const float *square_avg, const int32_t *last_step, int64_t N, int D, int step, float alpha, float *out_cn,
+                          void *stream);
+int read_compact_touched(const float *grad_nd, const unsigned char *touched, int64_t N, int D, int32_t *count, int capacity,
+                         int32_t *out_ids, float *out_grads, void *stream);
+int read_scatter_pairs(const int32_t *ids, const float *grads, int n, int D, int64_t N, float *grad_nd, unsigned char *touched,
+                       void *stream);
+
 /* Counts kernels launched by this library since load (bench.py's gpu_launches claim). */
 int64_t read_launch_count(void);
 

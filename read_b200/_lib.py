@@ -65,6 +65,12 @@ _SIGS = {
     "read_raster_derive_levels": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_sorted": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "read_raster_project_sorted_views": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "read_gather_backward_sparse": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "read_sparse_rmsprop_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_float, c_vp]),
+    "read_square_avg_dense": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, ctypes.c_float, c_vp, c_vp]),
+    "read_compact_touched": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "read_scatter_pairs": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "read_ipc_alloc": (c_int, [c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "read_ipc_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "read_ipc_close": (c_int, [c_vp]),

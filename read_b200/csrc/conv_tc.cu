@@ -112,6 +112,7 @@ struct TcArgs {
     int merge_done;                       // resident weights, kchunks == 1, mt == 1: ONE "tile done" commit per tile - the producers wait
                                           // on the accumulator's tfull barrier (A stage j of issuer me <-> accumulator slot 2j + me)
     int bpair;                            // streamed weights: one tcgen05.commit per PAIR of B stages
+    int probe;                            // issuers try_wait the NEXT tile's barriers before issuing the current tile's MMAs
     unsigned long long *trace;            // READ_DIAG builds: per-role timeline buffer (see TC_TRACE), else null
 };
 
@@ -370,6 +371,8 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         // all work disabled, so with one slot per issuer every small-tile layer ran at the chain's latency.
         uint32_t acc_c = 0, acc_p = 0;
         const uint32_t MT = (uint32_t)a.mt;
+        const bool probe = RES && a.probe != 0;       // host: resident weights, one K chunk, plain tiles
+        bool ready_t = false, ready_a = false;
         const uint32_t mt16 = (uint32_t)TC_TW * px16;                 // +1 M tile inside the supertile's halo, 16-byte units
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
             // a supertile owns MT consecutive accumulator slots (nacc % MT == 0: it never straddles the ring's wrap)
@@ -377,13 +380,24 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             acc_c += MT;
             if (acc_c >= (uint32_t)a.nacc) { acc_c = 0; acc_p ^= 1u; }
             if (a.dual ? ((tile_it & 1u) != me) : (me != 0u)) continue;   // not this issuer's supertile
-            for (uint32_t mi = 0; mi < MT; ++mi) mbar_wait(tempty0 + 8 * (acc + mi), acc_ph ^ 1u);
+            if (!(probe && ready_t))
+                for (uint32_t mi = 0; mi < MT; ++mi) mbar_wait(tempty0 + 8 * (acc + mi), acc_ph ^ 1u);
             TC_TRACE(2 + me, 3);
             tcgen05_fence_after();
             const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)a.n_tile;
             uint32_t bkc = b_lo0;                                      // resident weights: chunk kc of tap 0
             for (int kc = 0; kc < a.kchunks; ++kc, bkc += b16) {
-                mbar_wait(afull0 + 8 * (ring_bar + as), aph);
+                if (!(probe && ready_a)) mbar_wait(afull0 + 8 * (ring_bar + as), aph);
+                if (probe) {
+                    // look at the NEXT own tile's barriers now: their ~90-cycle try_wait latency overlaps the MMAs still queued in the
+                    // tensor pipe instead of sitting between this tile's last MMA and the next tile's first
+                    uint32_t an = acc + (a.dual ? 2u : 1u), apn = acc_ph;
+                    if (an >= (uint32_t)a.nacc) { an -= (uint32_t)a.nacc; apn ^= 1u; }
+                    uint32_t sn = as + 1u, spn = aph;
+                    if (sn == ring_n) { sn = 0; spn ^= 1u; }
+                    ready_t = __all_sync(0xFFFFFFFFu, mbar_try_wait(tempty0 + 8 * an, apn ^ 1u));
+                    ready_a = __all_sync(0xFFFFFFFFu, mbar_try_wait(afull0 + 8 * (ring_bar + sn), spn));
+                }
                 TC_TRACE(2 + me, 4);
                 tcgen05_fence_after();
                 const bool last_kc = kc == a.kchunks - 1;
@@ -487,13 +501,14 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             const uint32_t item_step = 4u >> lg;               // M tiles between two items of this warp
             const uint32_t n_units = (uint32_t)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // this CTA's supertiles
             const uint32_t n_mtiles = n_units << a.mt_log2;
+            // accumulator slot / phase of item `it`: it % nacc, (it / nacc) & 1 - kept incrementally (nacc need not be a power of two)
+            uint32_t acc = ((uint32_t)sub >> lg) % (uint32_t)a.nacc, acc_ph = (((uint32_t)sub >> lg) / (uint32_t)a.nacc) & 1u;
             for (uint32_t it = (uint32_t)sub >> lg; it < n_mtiles; it += item_step) {
                 const uint32_t su = it >> a.mt_log2, mi = it & (uint32_t)(a.mt - 1);
                 const TileCoord tc_ = decode_supertile((int)(blockIdx.x + su * gridDim.x), a);
                 const int b = tc_.b;
                 const int x = (tc_.tx + (int)mi) * TC_TW + px, y = tc_.ty * TC_TH + py;
                 const bool inside = (x < a.W) && (y < a.H);
-                const uint32_t acc = it & (uint32_t)(a.nacc - 1), acc_ph = (it >> a.nacc_log2) & 1u;   // nacc is a power of two
                 const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
                 const int co = chunk * 16;                                              // lean layers have ONE n tile
                 const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;                  // < 2^31 (checked by the host)
@@ -579,7 +594,8 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                     }
                 }
                 TC_TRACE(warp, 8);
-                TC_TRACE(warp, 8);
+                acc += item_step;
+                while (acc >= (uint32_t)a.nacc) { acc -= (uint32_t)a.nacc; acc_ph ^= 1u; }
             }
         } else
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x)
@@ -794,7 +810,7 @@ struct TcGeom {
 // Issue-side tuning, read at plan creation (read_set_option).  Measured ABAB on the C3 layers (profiles/r02_conv_experiments.md):
 //   tc_merge_done 1: ONE tcgen05.commit per tile for resident-weight, single-K-chunk layers (C=32: 87 -> 79 us, 97 -> 87 us)
 //   tc_commit_late / tc_bpair: fewer commits for supertiles / streamed weights - no gain, off
-int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0;
+int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0, g_tc_probe = 1;
 int g_tc_mt = 1;          // supertile width (read_set_option "tc_mt"): 1 = plain 8x16 tiles (default: measured fastest), 0 = auto-widen, 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
 static int desc_chan_gran(const read_conv_desc &d)
@@ -1038,11 +1054,15 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     if (a.dual) a.a_stages &= ~1;            // two equal half rings
     a.commit_late = g_tc_commit_late ? 1 : 0;
     a.merge_done = 0;
-    if (g_tc_merge_done && a.b_resident && g.kchunks == 1 && mt == 1 && a.a_stages >= a.nacc) {
-        a.merge_done = 1;                    // A ring depth == accumulator ring depth: stage <-> slot is one-to-one
-        a.a_stages = a.nacc;
-        a.dual = a.nacc >= 4 ? 1 : 0;
+    if (g_tc_merge_done && a.b_resident && g.kchunks == 1 && mt == 1 && a.a_stages >= 2) {
+        // A ring depth == accumulator ring depth: stage <-> slot is one-to-one.  The shallower ring wins (C=64: 144 KB of
+        // resident weights leave 3 A stages, so 3 of the 4 accumulator slots are used); two issuers need an even split.
+        a.merge_done = 1;
+        const int depth = a.a_stages < a.nacc ? a.a_stages : a.nacc;
+        a.dual = depth >= 4 ? 1 : 0;
+        a.a_stages = a.nacc = a.dual ? (depth & ~1) : depth;
     }
+    a.probe = (g_tc_probe && a.b_resident && g.kchunks == 1 && mt == 1) ? 1 : 0;
     a.bpair = 0;
     if (g_tc_bpair && !a.b_resident && a.b_stages >= 4) {
         a.bpair = 1;

@@ -124,33 +124,6 @@ __global__ void gather_backward_kernel(const float *__restrict__ go, const float
 // z-buffer derives levels 1..3 (2x2 min, see raster.cu: zbuf_derive_kernel), stores them, gathers the descriptors of
 // all four levels into the net's NHWC input buffers, and optionally resets level 0 to "empty" for the next frame
 // (replaces 3 derive + 4 gather + 1 clear launches).  One warp = one 8x8 block of level-0 pixels; lane = (row, 2 cols).
-template <typename TO>
-__device__ __forceinline__ void store_desc8(TO *out, long long pix, const float *tex, long long N, unsigned long long key);
-
-template <>
-__device__ __forceinline__ void store_desc8<__nv_bfloat16>(__nv_bfloat16 *out, long long pix, const float *tex, long long N,
-                                                           unsigned long long key)
-{
-    long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
-    if (id >= N) id = N - 1;
-    const float4 *t = reinterpret_cast<const float4 *>(tex + id * 8);
-    const float4 a = __ldg(t), c = __ldg(t + 1);
-    __nv_bfloat162 r[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w), __floats2bfloat162_rn(c.x, c.y),
-                           __floats2bfloat162_rn(c.z, c.w)};
-    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(r);
-}
-template <>
-__device__ __forceinline__ void store_desc8<float>(float *out, long long pix, const float *tex, long long N,
-                                                   unsigned long long key)
-{
-    long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
-    if (id >= N) id = N - 1;
-    const float4 *t = reinterpret_cast<const float4 *>(tex + id * 8);
-    float4 *o = reinterpret_cast<float4 *>(out + pix * 8);
-    o[0] = __ldg(t);
-    o[1] = __ldg(t + 1);
-}
-
 __device__ __forceinline__ void load_desc8(const float *tex, long long N, unsigned long long key, float4 (&d)[2])
 {
     long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
@@ -173,7 +146,8 @@ template <> __device__ __forceinline__ void write_desc8<float>(float *out, long 
     o[1] = d[1];
 }
 
-int g_gather_variant = 0;     // read_set_option("gather_variant"): 0 = gathers next to their stores, 1 / 2 = all gathers hoisted (64 regs / free)
+int g_gather_variant = 3;     // read_set_option("gather_variant"): 3 = the round-1 kernel (default: 42 us at C3); 0 / 1 / 2 = restructured variants
+                              // (gathers hoisted above the stores; measured 132 - 164 us, profiles/r02_raster.md) kept for A/B only
 
 struct FusedArgs {
     const float *tex;
@@ -269,6 +243,85 @@ __global__ void __launch_bounds__(256, V == 1 ? 4 : 1) pyramid_resolve_gather_ke
             const long long p3i = ((long long)b * H3 + (y >> 3)) * W3 + (x >> 3);
             a.z[3][p3i] = m3;
             write_desc8<TO>(static_cast<TO *>(a.out[3]), p3i, d4);
+        }
+    }
+}
+
+// the production kernel (gather_variant 3, unchanged since round 1)
+template <typename TO>
+__device__ __forceinline__ void store_desc8(TO *out, long long pix, const float *tex, long long N, unsigned long long key);
+
+template <>
+__device__ __forceinline__ void store_desc8<__nv_bfloat16>(__nv_bfloat16 *out, long long pix, const float *tex, long long N,
+                                                           unsigned long long key)
+{
+    long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
+    if (id >= N) id = N - 1;
+    const float4 *t = reinterpret_cast<const float4 *>(tex + id * 8);
+    const float4 a = __ldg(t), c = __ldg(t + 1);
+    __nv_bfloat162 r[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w), __floats2bfloat162_rn(c.x, c.y),
+                           __floats2bfloat162_rn(c.z, c.w)};
+    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(r);
+}
+template <>
+__device__ __forceinline__ void store_desc8<float>(float *out, long long pix, const float *tex, long long N,
+                                                   unsigned long long key)
+{
+    long long id = (key == ZBUF_EMPTY) ? 0ll : (long long)(key & 0xFFFFFFFFull);
+    if (id >= N) id = N - 1;
+    const float4 *t = reinterpret_cast<const float4 *>(tex + id * 8);
+    float4 *o = reinterpret_cast<float4 *>(out + pix * 8);
+    o[0] = __ldg(t);
+    o[1] = __ldg(t + 1);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) pyramid_resolve_gather_r1_kernel(const __grid_constant__ FusedArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int bw = a.W >> 3, bh = a.H >> 3;
+    const long long nblocks = (long long)a.B * bw * bh;
+    const int row = lane >> 2, col = (lane & 3) * 2;
+    for (long long blk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; blk < nblocks;
+         blk += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int bx = (int)(blk % bw);
+        long long t = blk / bw;
+        const int by = (int)(t % bh);
+        const int b = (int)(t / bh);
+        const int x = bx * 8 + col, y = by * 8 + row;
+        const long long p0 = ((long long)b * a.H + y) * a.W + x;
+        unsigned long long *zp = a.z[0] + p0;
+        const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(zp);            // x is even, level base is 16B aligned
+        if (a.reset0) *reinterpret_cast<ulonglong2 *>(zp) = make_ulonglong2(ZBUF_EMPTY, ZBUF_EMPTY);
+        TO *o0 = static_cast<TO *>(a.out[0]);
+        store_desc8<TO>(o0, p0, a.tex, a.N, k.x);
+        store_desc8<TO>(o0, p0 + 1, a.tex, a.N, k.y);
+        // level 1: 2x2 min = horizontal pair (in-lane) + vertical pair (lane ^ 4)
+        unsigned long long m1 = umin64(k.x, k.y);
+        m1 = umin64(m1, shfl_xor64(m1, 4));
+        // level 2: level-1 neighbours: horizontal lane ^ 1, vertical lane ^ 8
+        unsigned long long m2 = umin64(m1, shfl_xor64(m1, 1));
+        m2 = umin64(m2, shfl_xor64(m2, 8));
+        // level 3: horizontal lane ^ 2, vertical lane ^ 16
+        unsigned long long m3 = umin64(m2, shfl_xor64(m2, 2));
+        m3 = umin64(m3, shfl_xor64(m3, 16));
+        if ((row & 1) == 0) {
+            const int W1 = a.W >> 1, H1 = a.H >> 1;
+            const long long p1 = ((long long)b * H1 + (y >> 1)) * W1 + (x >> 1);
+            a.z[1][p1] = m1;
+            store_desc8<TO>(static_cast<TO *>(a.out[1]), p1, a.tex, a.N, m1);
+            if ((row & 2) == 0 && (lane & 1) == 0) {
+                const int W2 = a.W >> 2, H2 = a.H >> 2;
+                const long long p2 = ((long long)b * H2 + (y >> 2)) * W2 + (x >> 2);
+                a.z[2][p2] = m2;
+                store_desc8<TO>(static_cast<TO *>(a.out[2]), p2, a.tex, a.N, m2);
+                if (lane == 0) {
+                    const int W3 = a.W >> 3, H3 = a.H >> 3;
+                    const long long p3 = ((long long)b * H3 + (y >> 3)) * W3 + (x >> 3);
+                    a.z[3][p3] = m3;
+                    store_desc8<TO>(static_cast<TO *>(a.out[3]), p3, a.tex, a.N, m3);
+                }
+            }
         }
     }
 }
@@ -420,7 +473,8 @@ int read_pyramid_resolve_gather(const float *tex_nd, int D, int64_t N, uint64_t 
     const long long cap = (long long)num_sms() * 16;
     if (ctas > cap) ctas = cap;
     const int v = g_gather_variant;
-#define RB_PRG(T_) do { if (v == 1) pyramid_resolve_gather_kernel<T_, 1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
+#define RB_PRG(T_) do { if (v == 3) pyramid_resolve_gather_r1_kernel<T_><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
+                        else if (v == 1) pyramid_resolve_gather_kernel<T_, 1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
                         else if (v == 2) pyramid_resolve_gather_kernel<T_, 2><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); \
                         else pyramid_resolve_gather_kernel<T_, 0><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a); } while (0)
     if (layout == READ_FEAT_NHWC_BF16) RB_PRG(__nv_bfloat16);

@@ -26,6 +26,15 @@ from .compose import NetAndTexture
 
 TextureOptimizerClass = optim.RMSprop        # the descriptor optimizer the reference uses (ogl.py:16)
 
+
+def _texture_optimizer(args, textures, lr):
+    """The reference's dense RMSprop, or (default) read_b200.train.SparseRMSprop: same update, applied only to the points a batch
+    touched, fed by the sparse gather backward (``--dense_texture_optimizer`` keeps torch's)."""
+    if getattr(args, 'dense_texture_optimizer', False):
+        return TextureOptimizerClass([{'params': t.parameters()} for t in textures], lr=lr)
+    from .train import SparseRMSprop
+    return SparseRMSprop(list(textures), lr=lr)
+
 # (flag, kwargs, registered through parser.add - the reference's "also store in the yaml config" alias - or add_argument)
 _CLI = (
     ('--descriptor_size', dict(type=int, default=8), False),
@@ -34,6 +43,7 @@ _CLI = (
     ('--texture_lr', dict(type=float, default=1e-1), True),
     ('--texture_activation', dict(type=str, default='none'), True),
     ('--n_points', dict(type=int, default=0, help='this is for inference'), True),
+    ('--dense_texture_optimizer', dict(action='store_true', help='torch.optim.RMSprop over all points instead of the sparse kernel'), False),
 )
 
 
@@ -122,8 +132,7 @@ class TexturePipeline(Pipeline):
             textures[ds.id] = get_texture(args.descriptor_size, cloud['xyz'].shape[0], args)
         self.optimizer = optim.Adam(self.net.parameters(), lr=args.lr)
         # a single scene keeps ONE descriptor optimizer alive so that its running averages survive across epochs
-        self._extra_optimizer = (TextureOptimizerClass(textures[0].parameters(), lr=args.texture_lr)
-                                 if len(textures) == 1 else None)
+        self._extra_optimizer = _texture_optimizer(args, [textures[0]], args.texture_lr) if len(textures) == 1 else None
         self.criterion = args.criterion_module(**args.criterion_args).cuda()
         return textures
 
@@ -151,7 +160,7 @@ class TexturePipeline(Pipeline):
     def extra_optimizer(self, dataset):
         lr = self._texture_lr()
         if self._extra_optimizer is None:
-            return TextureOptimizerClass([{'params': self.textures[ds.id].parameters()} for ds in dataset], lr=lr)
+            return _texture_optimizer(self.args, [self.textures[ds.id] for ds in dataset], lr)
         self._extra_optimizer.param_groups[0]['lr'] = lr
         return self._extra_optimizer
 

@@ -75,6 +75,22 @@ def camera_batch(W, H, ts, znear=0.1, zfar=1000.0):
     return np.repeat(proj[None], len(ts), 0), view
 
 
+def crop_cameras(W, H, ts, rng, znear=0.1, zfar=1000.0):
+    """Training crops (configs/train_example.yaml:30-31: random zoom U(0.7, 2.0) and shift of the view before cropping): one
+    projection per crop with the focal length scaled by the zoom and the principal point shifted by up to a quarter frame."""
+    projs = []
+    for _ in ts:
+        K = intrinsics(W, H)
+        zoom = rng.uniform(0.7, 2.0)
+        K[0, 0] *= zoom
+        K[1, 1] *= zoom
+        K[0, 2] += rng.uniform(-0.25, 0.25) * W
+        K[1, 2] += rng.uniform(-0.25, 0.25) * H
+        projs.append(get_proj_matrix(K, (W, H), znear, zfar).astype(np.float32))
+    view = np.stack([camera_pose(t) for t in ts]).astype(np.float32)
+    return np.stack(projs), view
+
+
 def total_matrix(proj, view):
     """proj @ inv(view) in float32 with the same numpy call as src/READ/gl/myrender.py:28-30."""
     return (np.asarray(proj, np.float32) @ np.linalg.inv(np.asarray(view, np.float32))).astype(np.float32)

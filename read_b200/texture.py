@@ -58,6 +58,7 @@ class PointTexture(Texture):
         self.texture_ = descriptors
         self.activation, self.reg_weight = activation, reg_weight
         self._shadow = self._shadow_key = None          # point-major copy for the gather kernels, see point_major()
+        self._sparse, self._sparse_requested = None, False     # read_b200.train: sparse gradient accumulator
 
     def null_grad(self):
         self.texture_.grad = None
@@ -88,7 +89,14 @@ class PointTexture(Texture):
             raise RuntimeError("read_b200.PointTexture: texture must be on a CUDA device (no CPU fallback)")
         ids = ids.to(self.texture_.device, torch.float32).contiguous()
         if torch.is_grad_enabled() and self.texture_.requires_grad:
-            sample = _Gather.apply(self.texture_, ids)
+            if getattr(self, '_sparse_requested', False):
+                # training with read_b200.train.SparseRMSprop: the backward scatter-adds into a persistent point-major accumulator
+                # and flags the touched points; texture_.grad is never materialised
+                from . import train
+                train.enable_sparse_grad(self)
+                sample = train._GatherSparse.apply(self.texture_, ids, self)
+            else:
+                sample = _Gather.apply(self.texture_, ids)
             if self.activation == 'sigmoid':
                 return torch.sigmoid(sample)
             if self.activation == 'tanh':

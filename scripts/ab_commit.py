@@ -23,7 +23,7 @@ def setopt(**kw):
 
 
 def mk(**opts):
-    base = dict(tc_mt=1, tc_commit_late=0, tc_merge_done=0, tc_bpair=0, tc_role_rot=1, tc_pdl=0)
+    base = dict(tc_mt=1, tc_commit_late=0, tc_merge_done=0, tc_bpair=0, tc_probe=0, tc_role_rot=1, tc_pdl=0)
     base.update(opts)
     setopt(**base)
     e = UNetEngine(sd, 1, H, W, dev, precision="bf16", use_graph=False)
@@ -39,8 +39,7 @@ def t1(fn):
     return a.elapsed_time(b)
 
 
-variants = [("base", mk()), ("merge_done", mk(tc_merge_done=1)), ("mt4 late", mk(tc_mt=4, tc_commit_late=1)),
-            ("mt4 early", mk(tc_mt=4)), ("bpair", mk(tc_bpair=1))]
+variants = [("base", mk()), ("merge", mk(tc_merge_done=1)), ("probe", mk(tc_probe=1)), ("merge+probe", mk(tc_merge_done=1, tc_probe=1))]
 setopt(tc_pdl=0)
 sp = L.stream_ptr()
 ref = variants[0][1].output.clone()
@@ -57,6 +56,6 @@ for name in PICK:
     row = {k: round(float(np.median(v[2:])), 1) for k, v in ts.items()}
     out[name] = row
     print(f"{name:30s}", row, flush=True)
-setopt(tc_mt=1, tc_commit_late=0, tc_merge_done=0, tc_bpair=0, tc_pdl=1)
+setopt(tc_mt=1, tc_commit_late=0, tc_merge_done=1, tc_bpair=0, tc_probe=1, tc_pdl=1)
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)
