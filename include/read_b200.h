@@ -41,7 +41,8 @@ const char *read_last_error(void);
  *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = auto), "raster_stream" (1),
  *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0)
  *   convs:      read when a plan is created: "tc_mt" (supertile width 1 (default) / 2 / 4, 0 = auto-widen), "tc_merge_done" (1),
- *               "tc_commit_late" (0), "tc_bpair" (0); read at launch: "tc_role_rot" (1), "tc_pdl" (1: programmatic dependent
+ *               "tc_commit_late" (0), "tc_bpair" (0), "tc_probe" (0), "tc_pair" (1: CTA-pair cta_group::2 kernel for the Cin 64 layers,
+ *               2: every eligible layer, 0: off); read at launch: "tc_role_rot" (1), "tc_pdl" (1: programmatic dependent
  *               launch between consecutive conv kernels)
  * The options are process-wide tuning state (plain ints): set them before creating plans / launching, not concurrently with
  * launches from other threads.  Diagnostic knobs that skip work and therefore corrupt the output ("tc_debug", "tcg_debug",

@@ -75,6 +75,13 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st);
 void tc_plan_destroy(TcPlan *p);
 
 
+// tcgen05 CTA-pair path (conv_tc2.cu): cta_group::2 MMAs for the small-channel 3x3 layers
+struct Tc2Plan;
+bool tc2_supported(const read_conv_desc &d);
+int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out);
+int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st);
+void tc2_plan_destroy(Tc2Plan *p);
+
 // tcgen05 path with gathered A operand (conv_tc_gather.cu)
 struct TcgPlan;
 bool tcg_supported(const read_conv_desc &d);

@@ -810,7 +810,8 @@ struct TcGeom {
 // Issue-side tuning, read at plan creation (read_set_option).  Measured ABAB on the C3 layers (profiles/r02_conv_experiments.md):
 //   tc_merge_done 1: ONE tcgen05.commit per tile for resident-weight, single-K-chunk layers (C=32: 87 -> 79 us, 97 -> 87 us)
 //   tc_commit_late / tc_bpair: fewer commits for supertiles / streamed weights - no gain, off
-int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0, g_tc_probe = 1;
+int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0, g_tc_probe = 0;
+int g_tc_pair = 1;        // CTA-pair (cta_group::2) kernel, conv_tc2.cu (read_set_option "tc_pair"): 0 = off, 1 = Cin 64 layers, 2 = every eligible layer
 int g_tc_mt = 1;          // supertile width (read_set_option "tc_mt"): 1 = plain 8x16 tiles (default: measured fastest), 0 = auto-widen, 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
 static int desc_chan_gran(const read_conv_desc &d)
@@ -912,6 +913,7 @@ struct TcPlan {
     CUtensorMap tmB;
     TcArgs args;
     size_t smem_bytes;
+    Tc2Plan *pair;           // CTA-pair variant (conv_tc2.cu) when the layer qualifies and "tc_pair" is on
 };
 
 int tc_plan_create(const read_conv_desc &d, TcPlan **out)
@@ -932,6 +934,12 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     RB_CHECK_ARG(d.addin == nullptr || (reinterpret_cast<uintptr_t>(d.addin) & 15) == 0, "tcgen05 conv: addin must be 16B aligned");
     TcPlan *p = new (std::nothrow) TcPlan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
+    // measured ABAB at C3 (profiles/r02_conv_experiments.md): the pair kernel takes the C=64 layers from 73 to 56-68 us, but the C=32
+    // layers (HBM-bound at 3-4.5 TB/s, they live on bytes in flight, not on tensor cycles) from 86 to 97 us -> pairs for Cin 64 only
+    if (g_tc_pair && tc2_supported(d) && d.out_mode == READ_OUT_NHWC && (d.Cin == 64 || g_tc_pair >= 2)) {
+        const int rc2 = tc2_plan_create(d, &p->pair);
+        if (rc2 != READ_OK) { delete p; return rc2; }
+    }
 
     const bool s2 = d.stride == 2;
     const int halo_rows = s2 ? TC_TH + 1 : TC_TH + d.k - 1;
@@ -1092,6 +1100,7 @@ int g_tc_pdl = 1;         // programmatic dependent launch between consecutive c
 
 int tc_plan_launch(const TcPlan *p, cudaStream_t st)
 {
+    if (p->pair != nullptr) return tc2_plan_launch(p->pair, st);
     TcArgs a = p->args;
     a.debug = g_tc_debug;
     a.role_rot = g_tc_role_rot ? 1 : 0;
@@ -1162,7 +1171,11 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     return READ_OK;
 }
 
-void tc_plan_destroy(TcPlan *p) { delete p; }
+void tc_plan_destroy(TcPlan *p)
+{
+    if (p && p->pair) tc2_plan_destroy(p->pair);
+    delete p;
+}
 
 }  // namespace rb
 

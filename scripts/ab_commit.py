@@ -12,9 +12,8 @@ sd = synth.synth_state_dict(synth.SEED)
 H, W = 1088, 1920
 g = torch.Generator().manual_seed(3)
 feats = [torch.rand((1, 8, H >> l, W >> l), generator=g) for l in range(4)]
-PICK = ["Encoder.0.layers.0.main.0", "Encoder.0.layers.0.main.1", "Encoder.1.layers.0.main.0", "Encoder.2.layers.0.main.0",
-        "Encoder.2.layers.0.main.1", "Encoder.3.layers.0.main.0", "Encoder.3.layers.0.main.1", "FAM2.merge", "Convs.2",
-        "AFFs.0.conv.0", "feat_extract.1", "Convs.0"]
+PICK = ["Encoder.0.layers.0.main.0", "Encoder.0.layers.0.main.1", "Encoder.1.layers.0.main.0", "Encoder.1.layers.0.main.1",
+        "Decoder.3.layers.1.main.0", "Decoder.2.layers.1.main.1", "FAM2.merge", "AFFs.0.conv.1", "AFFs.1.conv.1", "Encoder.2.layers.0.main.0"]
 
 
 def setopt(**kw):
@@ -23,7 +22,7 @@ def setopt(**kw):
 
 
 def mk(**opts):
-    base = dict(tc_mt=1, tc_commit_late=0, tc_merge_done=0, tc_bpair=0, tc_probe=0, tc_role_rot=1, tc_pdl=0)
+    base = dict(tc_mt=1, tc_commit_late=0, tc_merge_done=1, tc_bpair=0, tc_probe=0, tc_pair=0, tc_role_rot=1, tc_pdl=0)
     base.update(opts)
     setopt(**base)
     e = UNetEngine(sd, 1, H, W, dev, precision="bf16", use_graph=False)
@@ -39,7 +38,7 @@ def t1(fn):
     return a.elapsed_time(b)
 
 
-variants = [("base", mk()), ("merge", mk(tc_merge_done=1)), ("probe", mk(tc_probe=1)), ("merge+probe", mk(tc_merge_done=1, tc_probe=1))]
+variants = [("no merge", mk(tc_merge_done=0)), ("merge", mk()), ("pair", mk(tc_pair=2))]
 setopt(tc_pdl=0)
 sp = L.stream_ptr()
 ref = variants[0][1].output.clone()
@@ -56,6 +55,6 @@ for name in PICK:
     row = {k: round(float(np.median(v[2:])), 1) for k, v in ts.items()}
     out[name] = row
     print(f"{name:30s}", row, flush=True)
-setopt(tc_mt=1, tc_commit_late=0, tc_merge_done=1, tc_bpair=0, tc_probe=1, tc_pdl=1)
+setopt(tc_mt=1, tc_commit_late=0, tc_merge_done=1, tc_bpair=0, tc_probe=0, tc_pair=1, tc_pdl=1)
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)

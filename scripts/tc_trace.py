@@ -13,6 +13,7 @@ lib.read_set_trace_buffer.restype = None
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["Encoder.0.layers.0.main.0", "Encoder.0.layers.0.main.1", "Encoder.1.layers.0.main.0"]
 mt = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 L.check(lib.read_set_option(b"tc_mt", mt))
+L.check(lib.read_set_option(b"tc_pair", int(sys.argv[3]) if len(sys.argv) > 3 else 1))
 L.check(lib.read_set_option(b"tc_pdl", 0))
 eng = UNetEngine(synth.synth_state_dict(synth.SEED), 1, H, W, dev, precision="bf16", use_graph=False)
 for t in eng.inputs: t.uniform_(0, 1)
@@ -54,7 +55,7 @@ for n in names:
                 line += f"  ->{NAMES.get(c, c)}: {np.mean([d[i - 1] for i in sel]):7.0f}"
         print(line)
     # one role's raw timeline sample (issuer 0 and epilogue warp 4), events 40..60
-    for r in (0, 2, 4, 5):
+    for r in (0, 2, 4, 5, 12):
         cnt = int(tr[r, 0])
         if cnt < 60: continue
         ev = tr[r, 41:61]

@@ -365,3 +365,35 @@ def test_tcgen05_addin_gated_matches_torch(cout):
     assert torch.isfinite(got).all(), "outputs left unwritten"
     tol = 2 ** -8 * float(want.abs().max()) + 4e-3
     assert float((got - want).abs().max()) < tol
+
+
+# ---------------------------------------------------------------- CTA-pair kernel (conv_tc2.cu: tcgen05.mma.cta_group::2)
+PAIR_CASES = [
+    ("C32 16x32 exact tiles (2 pairs)", [(32, 16, 32, "id", 1)], 32, 3, True, {}),
+    ("C32 ragged 19x23, odd tile count", [(32, 19, 23, "id", 1)], 32, 3, False, {"residual": True}),
+    ("C32 one tile per image (a pair spans two images)", [(32, 16, 8, "id", 1)], 32, 3, True, {}),
+    ("C64 24x40", [(64, 24, 40, "id", 1)], 64, 3, True, {}),
+    ("C64 ragged + residual", [(64, 9, 17, "id", 1)], 64, 3, False, {"residual": True}),
+    ("C32 -> 16 channels", [(32, 33, 20, "id", 1)], 16, 3, True, {}),
+    ("C64 -> 32 channels, no activation", [(64, 20, 24, "id", 1)], 32, 3, False, {}),
+    ("persistent C32, 2560 tiles (17 pairs per cluster: rings wrap)", [(32, 512, 640, "id", 1)], 32, 3, True, {"residual": True}),
+    ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_tcgen05_cta_pair_matches_torch_and_the_single_cta_kernel(case):
+    """cta_group::2 variant: same tolerance as the single-CTA kernel against torch, and bit-identical to it (same K order)."""
+    lib = L.load()
+    _, srcs, cout, k, elu, kw = case
+    try:
+        L.check(lib.read_set_option(b"tc_pair", 2))                      # every eligible layer, C=32 included
+        got, want = run_conv(srcs, cout, k, 1, elu, True, TC, **kw)[:2]
+        L.check(lib.read_set_option(b"tc_pair", 0))
+        base = run_conv(srcs, cout, k, 1, elu, True, TC, **kw)[0]
+    finally:
+        L.check(lib.read_set_option(b"tc_pair", 1))
+    assert torch.isfinite(got).all(), "pair kernel left outputs unwritten (NaN sentinel)"
+    tol = 2 ** -8 * float(want.abs().max()) + 4e-3
+    assert float((got - want).abs().max()) < tol
+    assert torch.equal(got, base)
