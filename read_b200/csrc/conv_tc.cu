@@ -343,7 +343,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         const uint32_t me = (warp == 3) ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t row_bytes = KKN * 16u * 2u;                 // cin_blk bf16
-        constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
+        constexpr uint32_t layout_type = (KKN == 4) ? 2u : (KKN == 2 ? 4u : 6u);   // SWIZZLE_128B : SWIZZLE_64B : SWIZZLE_32B
         // SBO = stride between consecutive 8-row groups = one halo row (halo_w pixels)
         const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, (uint32_t)a.halo_w * row_bytes, layout_type) >> 32);
         const uint32_t desc_hi_b = (uint32_t)(make_kmajor_desc(0, 8u * row_bytes, layout_type) >> 32);   // weights: dense rows
@@ -781,7 +781,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
 __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__restrict__ wm, int Cout, int cout_pad, int Cin,
                                int k, int cin_blk, int n_tile, __nv_bfloat16 *__restrict__ out)
 {
-    const int kchunks = Cin / cin_blk;
+    const int kchunks = (Cin + cin_blk - 1) / cin_blk;       // Cin 8 with 16-channel K steps: the upper half of every row is zero
     const int n_total = 2 * cout_pad;
     const int half = n_tile / 2;
     const long long total = (long long)k * k * kchunks * n_total * cin_blk;
@@ -799,7 +799,7 @@ __global__ void pack_tc_kernel(const float *__restrict__ wf, const float *__rest
         const int c = kc * cin_blk + kk;
         const int ky = tap / k, kx = tap % k;
         const float *w = is_m ? wm : wf;
-        out[i] = __float2bfloat16_rn(co < Cout ? w[(((long long)co * Cin + c) * k + ky) * k + kx] : 0.f);
+        out[i] = __float2bfloat16_rn((co < Cout && c < Cin) ? w[(((long long)co * Cin + c) * k + ky) * k + kx] : 0.f);
     }
 }
 
@@ -828,6 +828,10 @@ static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g, int chan_gran = 64
     // stride 2 keeps four phase tiles per stage: 32-channel K chunks keep a 3-stage ring within shared memory
     if (Cin % 64 == 0 && stride == 1 && chan_gran % 64 == 0) cin_blk = 64;
     else if (Cin % 32 == 0) cin_blk = 32;
+    // 8- and 16-channel inputs (the descriptor pyramid itself: feat_extract.0, SCM*.main.0; SCM2.main.1): ONE 16-channel K step,
+    // 32-byte rows with SWIZZLE_32B.  An 8-channel tensor is loaded with a 16-channel box: the TMA unit zero-fills the
+    // out-of-range half of every row, the packed weights carry zeros there - no padded copy of the input exists anywhere.
+    else if ((Cin == 8 || Cin == 16) && stride == 1) cin_blk = 16;
     else return false;
     int cout_pad = Cout;
     if (Cout <= 8) cout_pad = 8;                 // final layer: N = 16 (f|m of 8 padded channels)
@@ -836,7 +840,8 @@ static bool tc_geom(int Cin, int Cout, int stride, TcGeom *g, int chan_gran = 64
     const int n_tile = n_total <= 256 ? n_total : 256;
     if (n_total % n_tile != 0) return false;
     if (cout_pad > 8 && (n_tile / 2) % 16 != 0) return false;
-    if (g) *g = TcGeom{cin_blk, Cin / cin_blk, n_tile, n_total / n_tile, cout_pad};
+    if (cin_blk == 16 && (n_total / n_tile != 1 || cout_pad <= 8 || !(cout_pad == 16 || cout_pad == 32 || cout_pad == 64))) return false;
+    if (g) *g = TcGeom{cin_blk, (Cin + cin_blk - 1) / cin_blk, n_tile, n_total / n_tile, cout_pad};
     return true;
 }
 
@@ -969,7 +974,8 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
         if (g_tc_mt == 1) mt = 1;
     }
     const int halo_w = s2 ? TC_TW + 1 : TC_TW * mt + d.k - 1;
-    const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw = g.cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (g.cin_blk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     for (int si = 0; si < d.n_src; ++si) {   // activations: dims {C, W, H, B}; box = one halo tile (all filter taps)
         const read_src &sv = d.src[si];
         const unsigned f = (d.n_src > 1 && sv.mode == READ_SRC_NEAREST_DOWN) ? (unsigned)sv.factor : (s2 ? 2u : 1u);
@@ -1148,11 +1154,19 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     // the two ResBlock layer kinds of the C=32 / C=64 stages get compile-time epilogues
     const int epi = (lean && a.stride == 1 && a.ksize == 3 && a.b_resident && !a.out2)
                         ? ((a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0)) : 0;
-    if (kkn != 2 && kkn != 4) {
+    if (kkn != 1 && kkn != 2 && kkn != 4) {
         set_error("tcgen05 conv: no kernel instance for cin_blk=%d", a.cin_blk);
         return READ_ERR_UNSUPPORTED;
     }
-    if (epi == 1 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 1, 1);
+    if (kkn == 1) {        // 8- / 16-channel inputs: resident weights, lean epilogue (tc_geom admits nothing else)
+        if (!(lean && a.b_resident && a.stride == 1)) {
+            set_error("tcgen05 conv: 16-channel K steps need resident weights and Cout 16 / 32 / 64");
+            return READ_ERR_UNSUPPORTED;
+        }
+        if (a.ksize == 3) { if (epi == 1) RB_TC_LAUNCH_I(3, 1, true, 640, 1, 1); else RB_TC_LAUNCH_I(3, 1, true, 640, 0, 1); }
+        else RB_TC_LAUNCH_I(1, 1, true, 640, 0, 1);
+    }
+    else if (epi == 1 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 1, 1);
     else if (epi == 2 && kkn == 2) RB_TC_LAUNCH_I(3, 2, true, 640, 2, 1);
     else if (epi == 1 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 1, 1);
     else if (epi == 2 && kkn == 4) RB_TC_LAUNCH_I(3, 4, true, 640, 2, 1);
@@ -1194,7 +1208,7 @@ int64_t read_tc_weight_elems(int Cout, int Cin, int k)
 {
     TcGeom g;
     if (!tc_geom(Cin, Cout, 1, &g)) return -1;
-    return (int64_t)k * k * Cin * 2 * g.cout_pad;
+    return (int64_t)k * k * g.kchunks * g.cin_blk * 2 * g.cout_pad;
 }
 
 int read_pack_weights_tc(const float *wf, const float *wm, int Cout, int Cin, int k, void *out_bf16, void *stream)
@@ -1223,7 +1237,7 @@ static int pack_tc_impl(const float *wf, const float *wm, int Cout, int Cin, int
     RB_CHECK_ARG(wf && wm && out_bf16, "pack_tc: null pointer");
     RB_CHECK_ARG(stride == 1 || stride == 2, "pack_tc: stride must be 1 or 2");
     RB_CHECK_ARG(tc_geom(Cin, Cout, stride, &g, chan_gran), "pack_tc: unsupported channel counts %d -> %d", Cin, Cout);
-    const long long total = (long long)k * k * Cin * 2 * g.cout_pad;
+    const long long total = (long long)k * k * g.kchunks * g.cin_blk * 2 * g.cout_pad;
     long long blocks = (total + 255) / 256;
     if (blocks > 65535) blocks = 65535;
     pack_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(wf, wm, Cout, g.cout_pad, Cin, k, g.cin_blk, g.n_tile,

@@ -36,15 +36,19 @@ namespace rb {
             a.trace[(role_) * 2048] = ++trc_n;                                                                          \
         }                                                                                                               \
     } while (0)
+#define T2_DBG(a_, bit_) (((a_).debug & (bit_)) != 0)     // tc_debug: 2 = no global stores, 32 = no residual loads (timing experiments)
 #else
 #define T2_TRACE(role_, code_) do { } while (0)
+#define T2_DBG(a_, bit_) false
 #endif
 
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the pair's EVEN (leader) CTA
 constexpr int T2_TW = 8, T2_TH = 16;
 constexpr int T2_MAX_SLOTS = 8;
 constexpr int T2_TMEM_COLS = 512;
-constexpr int B2_AFULL = 0, B2_TFULL = 8, B2_TEMPTY = 16, B2_BRES = 24, B2_TMEMPTR = 26, B2_PARAMS = 28;   // uint64 slots
+constexpr int B2_AFULL = 0, B2_TFULL = 8, B2_TEMPTY = 16, B2_BRES = 24, B2_TMEMPTR = 26, B2_RFULL = 28, B2_PARAMS = 76;   // uint64 slots
+constexpr int T2_STAGE_BYTES = 1024;              // one epilogue item: 32 pixels x 16 channels bf16, staged for the TMA store
+constexpr int T2_NBUF = 3;                        // staging buffers per epilogue warp (a residual tile is loaded one item ahead)
 
 struct Tc2Args {
     int B, H, W, Cin, Cout;
@@ -58,11 +62,13 @@ struct Tc2Args {
     uint32_t a_tx_bytes, a_bytes;             // halo tile bytes, rounded to 1 KB
     uint32_t b_half_bytes;                    // one tap's half weight tile: (n_tile / 2) x cin_blk bf16
     uint32_t b_region_off;
-    int elu, pdl;
+    uint32_t stage_off;                       // 16 warps x T2_NBUF x 1 KB staging buffers of the epilogue's TMA stores
+    int elu, pdl, tma_out;
     const float *bias_f, *bias_m, *scale, *shift;
     const __nv_bfloat16 *residual;
     __nv_bfloat16 *out;
     unsigned long long *trace;                // READ_DIAG builds only
+    int debug;                                // READ_DIAG builds only
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -149,14 +155,15 @@ __device__ __forceinline__ Tile2 decode2(int t, const Tc2Args &a)
 // KS = filter size, KKN = cin_blk / 16, EPI: 0 = runtime flags, 1 = ELU / no residual, 2 = no activation + residual
 template <int KS, int KKN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
-gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Tc2Args a)
+gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ Tc2Args a)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
     constexpr int ntaps = KS * KS;
     const uint32_t b_region = smem_base + a.b_region_off;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + (uint32_t)ntaps * a.b_half_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.stage_off + 16u * T2_NBUF * T2_STAGE_BYTES);
     const uint32_t bar0 = s_u32(bars);
     const uint32_t afull0 = bar0 + 8 * B2_AFULL, tfull0 = bar0 + 8 * B2_TFULL, tempty0 = bar0 + 8 * B2_TEMPTY, bres = bar0 + 8 * B2_BRES;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + B2_TMEMPTR);
@@ -175,6 +182,8 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        if (a.residual != nullptr) tma_prefetch_desc(&tmR);
     }
     const uint32_t items_per_tile = (uint32_t)(a.n_tile >> 3);              // 4 quadrants x nch16 chunks
     if (warp == 1 && lane == 0) {
@@ -184,6 +193,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             mbar_init(tempty0 + 8 * s, 2u * items_per_tile);               // both CTAs' epilogue items
         }
         mbar_init(bres, 1);
+        for (int i = 0; i < 16 * T2_NBUF; ++i) mbar_init(bar0 + 8 * (B2_RFULL + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc2(s_u32(tmem_ptr_smem), T2_TMEM_COLS);
@@ -222,9 +232,15 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             T2_TRACE(rank * 8, 2);
             if (++s == slots) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only) =====================
+    } else if (warp == 1 || warp == 3) {
+        // ===================== MMA issuers (leader CTA only): warps 1 and 3 take alternate units =====================
+        // Role timeline of the single-issuer version (profiles/r02_role_timelines.md): 574 + 370 cycles of barrier waits between
+        // the last MMA of a unit and the first of the next, during which the tensor pipe drains its short queue and idles
+        // (36 MMAs took 2085 cycles to issue, i.e. the issue is back-pressured by execution).  With two issuing threads the other
+        // one has finished its waits and sits at its first MMA while this one is still issuing.  A unit's slot is i % slots, so
+        // the issuers own disjoint slots (slots is even) and each commit covers exactly its own thread's MMAs.
         if (leader) {
+            const uint32_t me = warp == 3 ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((256u >> 4) << 24);
             constexpr uint32_t row_bytes = KKN * 16u * 2u;
             constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;         // SWIZZLE_128B : SWIZZLE_64B
@@ -236,14 +252,18 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_half_bytes >> 4;
             const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
             mbar_wait(bres, 0);
-            uint32_t s = 0, ph = 0, a_lo = a_lo0;
+            uint32_t s = 0, ph = 0;
             for (uint32_t i = 0; i < my_units; ++i) {
-                mbar_wait(tempty0 + 8 * s, ph ^ 1u);
-                T2_TRACE(2, 3);
-                mbar_wait(afull0 + 8 * s, ph);
-                T2_TRACE(2, 4);
+                const uint32_t s_i = s, ph_i = ph;
+                if (++s == slots) { s = 0; ph ^= 1u; }
+                if ((i & 1u) != me) continue;                           // the other issuer's unit
+                mbar_wait(tempty0 + 8 * s_i, ph_i ^ 1u);
+                T2_TRACE(2 + me, 3);
+                mbar_wait(afull0 + 8 * s_i, ph_i);
+                T2_TRACE(2 + me, 4);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + s * (uint32_t)a.n_tile;
+                const uint32_t d_tmem = tmem_base + s_i * (uint32_t)a.n_tile;
+                const uint32_t a_lo = a_lo0 + s_i * a16;
                 if (elect_one()) {
 #pragma unroll
                     for (int kx = 0; kx < KS; ++kx) {
@@ -256,12 +276,10 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                 umma2_bf16(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, (kx | ky | kk) != 0 ? 1u : 0u);
                         }
                     }
-                    umma2_commit_multicast(tfull0 + 8 * s);
+                    umma2_commit_multicast(tfull0 + 8 * s_i);
                 }
                 __syncwarp();
-                T2_TRACE(2, 5);
-                a_lo += a16;
-                if (++s == slots) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+                T2_TRACE(2 + me, 5);
             }
         }
     } else if (warp >= 4) {
@@ -283,6 +301,24 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int trole = (warp == 4 || warp == 5) ? (int)rank * 8 + warp : -1;
 #endif
         uint32_t acc = ((uint32_t)sub >> lg) % slots, acc_ph = (((uint32_t)sub >> lg) / slots) & 1u;
+        // Output path.  Round-2 timing experiments (scripts/ab_pair_dbg.py, profiles/r02_conv_experiments.md): with the epilogue's
+        // global stores switched off a C=64 layer ran in 50 instead of 64 us - a lane's two 16-byte stores at a 128-byte lane stride
+        // cost 32 LSU wavefronts per instruction.  The item (32 pixels x 16 channels = 1 KB) is therefore staged in a per-warp
+        // shared-memory buffer (conflict-free with the 32-byte TMA swizzle) and written by ONE TMA store per item; a residual tile
+        // is TMA-loaded into the same buffer one item ahead and updated in place.  No cross-warp synchronisation is involved: each
+        // warp's lane 0 owns its bulk groups.  Ragged edges and the phantom tile of an odd tile count are clipped by the TMA unit.
+        const uint32_t sbuf0 = smem_base + a.stage_off + (uint32_t)(warp - 4) * (T2_NBUF * T2_STAGE_BYTES);
+        const uint32_t rfull0 = bar0 + 8 * (B2_RFULL + (warp - 4) * T2_NBUF);
+        const uint32_t lane_off = (uint32_t)lane * 32u, sw = (((uint32_t)lane >> 2) & 1u) * 16u;     // SWIZZLE_32B: bit 4 ^= bit 7
+        const int co = chunk * 16;
+        uint32_t k = 0, kph = 0;                                                                      // staging buffer of this item
+        const bool tma_out = a.tma_out != 0;
+        if (tma_out && has_res && lane == 0 && ((uint32_t)sub >> lg) < my_units) {
+            const long long t0 = 2ll * ((long long)cluster_id + (long long)((uint32_t)sub >> lg) * n_clusters) + rank;
+            const Tile2 t0c = decode2((int)t0, a);
+            mbar_arrive_expect_tx(rfull0, T2_STAGE_BYTES);
+            tma_load_4d(&tmR, rfull0, sbuf0, co, t0c.tx * T2_TW, t0c.ty * T2_TH + q * 4, t0c.b);
+        }
         for (uint32_t it = (uint32_t)sub >> lg; it < my_units; it += item_step) {
             const long long t = 2ll * ((long long)cluster_id + (long long)it * n_clusters) + rank;
             const Tile2 tc = decode2((int)t, a);
@@ -290,10 +326,20 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int x = tc.tx * T2_TW + px, y = tc.ty * T2_TH + py;
             const bool inside = (t < a.n_tiles) && (x < a.W) && (y < a.H);
             const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
-            const int co = chunk * 16;
             const int o = ((b * a.H + y) * a.W + x) * a.Cout + co;
             uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0;
-            if (inside && has_res) {
+            const uint32_t kn = k + 1 == T2_NBUF ? 0u : k + 1;
+            if (tma_out) {
+                if (lane == 0) {
+                    bulk_wait_group_read<1>();          // only the previous item's store may still be reading: buffers k and kn are free
+                    if (has_res && it + item_step < my_units) {
+                        const long long tn = t + 2ll * (long long)item_step * n_clusters;
+                        const Tile2 tnc = decode2((int)tn, a);
+                        mbar_arrive_expect_tx(rfull0 + 8 * kn, T2_STAGE_BYTES);
+                        tma_load_4d(&tmR, rfull0 + 8 * kn, sbuf0 + kn * T2_STAGE_BYTES, co, tnc.tx * T2_TW, tnc.ty * T2_TH + q * 4, tnc.b);
+                    }
+                }
+            } else if (inside && has_res && !T2_DBG(a, 32)) {
                 rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
                 rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
             }
@@ -308,7 +354,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             T2_TRACE(trole, 7);
             // the accumulator is in registers: hand the TMEM slot back to the leader's issuer before the math
             tcgen05_fence_before();
-            __syncwarp();
+            __syncwarp();                               // (also orders lane 0's wait_group.read before the other lanes' staging writes)
             if (lane == 0) mbar_arrive_cluster((tempty0 + 8 * acc) & PEER_MASK);
             float yv[16];
             if (elu) {
@@ -318,7 +364,33 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
             }
-            if (inside) {
+            if (tma_out) {
+                const uint32_t sb = sbuf0 + k * T2_STAGE_BYTES + lane_off;
+                if (has_res) {
+                    mbar_wait(rfull0 + 8 * k, kph);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rs0.x), "=r"(rs0.y), "=r"(rs0.z), "=r"(rs0.w) : "r"(sb + sw));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rs1.x), "=r"(rs1.y), "=r"(rs1.z), "=r"(rs1.w) : "r"(sb + (sw ^ 16u)));
+                    const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        yv[2 * j] += __uint_as_float(rr[j] << 16);
+                        yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                    }
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = cvt2_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + sw), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (sw ^ 16u)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!T2_DBG(a, 2)) tma_store_4d(&tmO, sbuf0 + k * T2_STAGE_BYTES, co, tc.tx * T2_TW, tc.ty * T2_TH + q * 4, b);
+                    bulk_commit_group();
+                }
+                k = kn;
+                if (k == 0) kph ^= 1u;
+            } else if (inside && !T2_DBG(a, 2)) {
                 if (has_res) {
                     const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
 #pragma unroll
@@ -338,6 +410,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             acc += item_step;
             while (acc >= slots) { acc -= slots; acc_ph ^= 1u; }
         }
+        if (tma_out && lane == 0) bulk_wait_group<0>();          // the staging buffers are read, the stores performed, before the CTA retires
     }
 
     // nobody leaves while the peer may still signal this CTA's barriers or its TMEM is in use
@@ -357,7 +430,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 PFN_encodeTiled get_encode_tiled();           // conv_tc.cu
 
 struct Tc2Plan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmR;
     Tc2Args args;
     size_t smem_bytes;
     int kkn, epi;
@@ -418,6 +491,22 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
             return READ_ERR_CUDA;
         }
     }
+    {   // epilogue items: 16 channels x 8 x 4 pixels of the NHWC output (store) / of the residual tensor (load), 32-byte swizzle
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.Wout, (cuuint64_t)d.Hout, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)d.Wout * d.Cout * 2, (cuuint64_t)d.Hout * d.Wout * d.Cout * 2};
+        cuuint32_t box[4] = {16, (cuuint32_t)T2_TW, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = enc(&p->tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.residual ? const_cast<void *>(d.residual) : d.out, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tcgen05 pair conv: cuTensorMapEncodeTiled(output items) failed with %d", (int)r);
+            delete p;
+            return READ_ERR_CUDA;
+        }
+    }
     Tc2Args &a = p->args;
     a.B = d.B; a.H = d.Hout; a.W = d.Wout; a.Cin = d.Cin; a.Cout = d.Cout;
     a.ksize = d.k; a.pad = d.pad;
@@ -433,12 +522,17 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     a.b_half_bytes = (uint32_t)(n_tile / 2) * cin_blk * 2u;
     const int nacc = T2_TMEM_COLS / n_tile > T2_MAX_SLOTS ? T2_MAX_SLOTS : T2_TMEM_COLS / n_tile;
     a.slots = nacc;
+    {   // the A ring (one halo tile per accumulator slot) shares 227 KB with the resident weights and the epilogue's staging buffers
+        const size_t fixed = 1024 + (size_t)d.k * d.k * a.b_half_bytes + 16 * T2_NBUF * T2_STAGE_BYTES + 8 * B2_PARAMS + 16 * (size_t)d.Cout + 64;
+        while (a.slots > 2 && fixed + (size_t)a.slots * a.a_bytes > 227 * 1024) --a.slots;
+    }
     a.b_region_off = (uint32_t)a.slots * a.a_bytes;
+    a.stage_off = a.b_region_off + (uint32_t)(d.k * d.k) * a.b_half_bytes;          // a multiple of 1 KB (b_half_bytes is)
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
     a.out = static_cast<__nv_bfloat16 *>(d.out);
-    p->smem_bytes = 1024 + (size_t)a.b_region_off + (size_t)d.k * d.k * a.b_half_bytes + 8 * B2_PARAMS + 16 * (size_t)d.Cout + 64;
+    p->smem_bytes = 1024 + (size_t)a.stage_off + 16 * T2_NBUF * T2_STAGE_BYTES + 8 * B2_PARAMS + 16 * (size_t)d.Cout + 64;
     p->kkn = cin_blk / 16;
     p->epi = (a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0);
     if (p->smem_bytes > 227 * 1024) {
@@ -452,12 +546,16 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
 
 extern int g_tc_pdl;
 extern unsigned long long *g_tc_trace;
+extern int g_tc_debug;
+int g_tc_tma_store = 1;          // read_set_option "tc_tma_store": epilogue output through staged TMA stores (0: per-lane global stores)
 
 int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
 {
     Tc2Args a = p->args;
     a.pdl = g_tc_pdl ? 1 : 0;
     a.trace = g_tc_trace;
+    a.debug = g_tc_debug;
+    a.tma_out = g_tc_tma_store ? 1 : 0;
     if (a.n_tiles == 0) return READ_OK;
     long long grid = num_sms() & ~1;                  // whole pairs
     const long long units = (a.n_tiles + 1) / 2;
@@ -476,7 +574,7 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
     do {                                                                                                                \
         RB_CUDA(cudaFuncSetAttribute(gated_conv_tc2_kernel<3, KKN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)p->smem_bytes));                                                              \
-        RB_CUDA(cudaLaunchKernelEx(&lcfg, gated_conv_tc2_kernel<3, KKN_, EPI_>, p->tmA, p->tmB, a));                    \
+        RB_CUDA(cudaLaunchKernelEx(&lcfg, gated_conv_tc2_kernel<3, KKN_, EPI_>, p->tmA, p->tmB, p->tmO, p->tmR, a));                    \
     } while (0)
     if (p->kkn == 2) {
         if (p->epi == 1) RB_TC2(2, 1); else if (p->epi == 2) RB_TC2(2, 2); else RB_TC2(2, 0);

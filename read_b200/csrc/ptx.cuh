@@ -85,6 +85,28 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint32_t bar,
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// 4-D box shared -> global (TMA store, bulk-group completion).  The shared-memory source must have been made visible to the async
+// proxy (fence_proxy_async_smem) by the threads that wrote it; out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... may still be pending at all (writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // L2 prefetch of a 4-D box (no shared-memory destination, no barrier): warms L2 for a tile that will be loaded later
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
 {

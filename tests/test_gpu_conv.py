@@ -181,6 +181,14 @@ TC_CASES = [
     ("persistent C32, 2560 tiles (17 per CTA)", [(32, 512, 640, "id", 1)], 32, 3, True, {}),
     ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
     ("final layer 32->3, NCHW f32 output", [(32, 24, 40, "id", 1)], 3, 3, False, {"final": True}),
+    # 8- / 16-channel inputs: one 16-channel K step (SWIZZLE_32B rows); an 8-channel tensor is read with a 16-channel TMA box whose
+    # out-of-range half is zero-filled
+    ("first conv 8->32 (feat_extract.0), ragged", [(8, 20, 28, "id", 1)], 32, 3, True, {}),
+    ("SCM main.0 8->16", [(8, 33, 17, "id", 1)], 16, 3, True, {}),
+    ("SCM main.0 8->64 + residual-free no-act", [(8, 16, 24, "id", 1)], 64, 3, False, {}),
+    ("3x3 16->32", [(16, 19, 23, "id", 1)], 32, 3, True, {"residual": True}),
+    ("1x1 16->32 (SCM2.main.1)", [(16, 24, 40, "id", 1)], 32, 1, True, {}),
+    ("persistent 8->32, 2560 tiles", [(8, 512, 640, "id", 1)], 32, 3, True, {}),
     # the C3 shapes of the streamed-weight instances (B = 2): the B ring and the accumulator ring wrap many times per CTA
     ("persistent C128 @272x480 + residual (Encoder.2 at C3), 14 tiles per CTA", [(128, 272, 480, "id", 1)], 128, 3, False, {"residual": True}),
     ("persistent C128 @272x480 ELU", [(128, 272, 480, "id", 1)], 128, 3, True, {}),
@@ -253,7 +261,7 @@ def test_tc_supported_predicate():
     d.k, d.stride, d.pad, d.out_mode = 3, 1, 1, L.OUT_NHWC
     d.Hin = d.Hout = 8
     d.Win = d.Wout = 8
-    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]:   # (32,3) needs NCHW f32 output, see below
+    for cin, cout, ok in [(32, 32, 1), (64, 64, 1), (128, 128, 1), (256, 256, 1), (8, 32, 1), (16, 32, 1), (8, 128, 0), (32, 3, 0), (56, 64, 0), (480, 32, 1), (64, 32, 1)]:   # (32,3) needs NCHW f32 output, see below
         d.Cin, d.Cout = cin, cout
         assert lib.read_conv_tc_supported(ctypes.byref(d)) == ok, (cin, cout)
     d.Cin, d.Cout, d.out_mode = 32, 3, L.OUT_NCHW_F32
