@@ -62,12 +62,16 @@ constexpr int TC_TMEM_COLS = 512;
 // barrier slots (uint64 each)
 constexpr int TC_MAX_ACC = 8;               // TMEM accumulator ring: 512 columns / n_tile, at most 8
 constexpr int BAR_AFULL = 0, BAR_AEMPTY = 16, BAR_BFULL = 32, BAR_BEMPTY = 48, BAR_TFULL = 64, BAR_TEMPTY = 72,
-              BAR_BRES = 80, BAR_TMEMPTR = 82, BAR_PARAMS = 84;
+              BAR_BRES = 80, BAR_TMEMPTR = 82, BAR_RFULL = 84, BAR_PARAMS = 132;
+// lean epilogue output staging (see the item loop): 16 warps x TC_NBUF buffers of one item (32 pixels x 16 channels bf16 = 1 KB)
+constexpr int TC_STAGE_BYTES = 1024, TC_NBUF = 3;
+constexpr uint32_t TC_STAGING_BYTES = 16u * TC_NBUF * TC_STAGE_BYTES;
 
 // activation tensor maps: one per source of a virtual concat (1x1 convs: torch.cat along channels, unet.py:88,105,263;
 // a nearest-DOWN resampled source is a traversal-stride load of the full-resolution tensor)
 struct TcMaps {
     CUtensorMap a[READ_MAX_SRC];
+    CUtensorMap o, r;        // lean epilogue items of the NHWC output (TMA store) / the residual tensor (TMA load), when args.tma_out
 };
 
 struct TcArgs {
@@ -112,6 +116,8 @@ struct TcArgs {
     int merge_done;                       // resident weights, kchunks == 1, mt == 1: ONE "tile done" commit per tile - the producers wait
                                           // on the accumulator's tfull barrier (A stage j of issuer me <-> accumulator slot 2j + me)
     int bpair;                            // streamed weights: one tcgen05.commit per PAIR of B stages
+    int tma_out;                          // lean epilogue: items are staged in shared memory and written by TMA stores (plan: fits, no out2)
+    uint32_t stage_bytes;                 // TC_STAGING_BYTES when the plan reserved the staging buffers (between the B region and the barriers)
     int probe;                            // issuers try_wait the NEXT tile's barriers before issuing the current tile's MMAs
     unsigned long long *trace;            // READ_DIAG builds: per-role timeline buffer (see TC_TRACE), else null
 };
@@ -191,7 +197,8 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
     constexpr int ntaps = KS * KS;
     const uint32_t b_region = smem_base + a.b_region_off;
     const uint32_t b_region_bytes = RES ? (uint32_t)(ntaps * a.kchunks) * a.b_bytes : (uint32_t)a.b_stages * a.b_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + b_region_bytes);
+    const uint32_t stage_region = smem_base + a.b_region_off + b_region_bytes;            // 1 KB aligned (b_bytes is a multiple of 1 KB)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + b_region_bytes + a.stage_bytes);
     const uint32_t bar0 = s_u32(bars);
     const uint32_t afull0 = bar0 + 8 * BAR_AFULL, aempty0 = bar0 + 8 * BAR_AEMPTY;
     const uint32_t bfull0 = bar0 + 8 * BAR_BFULL, bempty0 = bar0 + 8 * BAR_BEMPTY;
@@ -220,6 +227,10 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < a.n_src; ++i) tma_prefetch_desc(&tm.a[i]);
         tma_prefetch_desc(&tmB);
+        if (a.tma_out) {
+            tma_prefetch_desc(&tm.o);
+            if (a.residual != nullptr) tma_prefetch_desc(&tm.r);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) {
@@ -233,6 +244,8 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             mbar_init(tempty0 + 8 * i, NTHR == 640 ? (a.raw ? 16u : (uint32_t)(a.n_tile >> 3)) : (NTHR - 128) / 32);   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
         }
         mbar_init(bres, 1);
+        if (NTHR == 640)
+            for (int i = 0; i < 16 * TC_NBUF; ++i) mbar_init(bar0 + 8 * (BAR_RFULL + i), 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(s_u32(tmem_ptr_smem), TC_TMEM_COLS);
@@ -503,6 +516,23 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             const uint32_t n_mtiles = n_units << a.mt_log2;
             // accumulator slot / phase of item `it`: it % nacc, (it / nacc) & 1 - kept incrementally (nacc need not be a power of two)
             uint32_t acc = ((uint32_t)sub >> lg) % (uint32_t)a.nacc, acc_ph = (((uint32_t)sub >> lg) / (uint32_t)a.nacc) & 1u;
+            // Output path (a.tma_out).  Timing experiments (scripts/ab_pair_dbg.py, profiles/r02_conv_experiments.md): a lane's two
+            // 16-byte stores at a Cout * 2 byte lane stride cost 32 LSU wavefronts per instruction and bounded the epilogue (C=32:
+            // 89 -> 65 us with the stores switched off).  The item (32 pixels x 16 channels = 1 KB) is staged in a per-warp buffer
+            // (conflict-free under the 32-byte TMA swizzle) and written by ONE TMA store; a residual tile is TMA-loaded into the same
+            // buffer one item ahead and updated in place.  No cross-warp synchronisation: each warp's lane 0 owns its bulk groups.
+            // Ragged edges are clipped by the TMA unit.
+            const bool tma_out = a.tma_out != 0;
+            const uint32_t sbuf0 = stage_region + (uint32_t)(warp - 4) * (TC_NBUF * TC_STAGE_BYTES);
+            const uint32_t rfull0 = bar0 + 8 * (BAR_RFULL + (warp - 4) * TC_NBUF);
+            const uint32_t lane_off = (uint32_t)lane * 32u, sw = (((uint32_t)lane >> 2) & 1u) * 16u;     // SWIZZLE_32B: bit 4 ^= bit 7
+            uint32_t kb = 0, kph = 0;
+            if (tma_out && has_res && lane == 0 && ((uint32_t)sub >> lg) < n_mtiles) {
+                const uint32_t it0 = (uint32_t)sub >> lg;
+                const TileCoord t0 = decode_supertile((int)(blockIdx.x + (it0 >> a.mt_log2) * gridDim.x), a);
+                mbar_arrive_expect_tx(rfull0, TC_STAGE_BYTES);
+                tma_load_4d(&tm.r, rfull0, sbuf0, chunk * 16, (t0.tx + (int)(it0 & (uint32_t)(a.mt - 1))) * TC_TW, t0.ty * TC_TH + q * 4, t0.b);
+            }
             for (uint32_t it = (uint32_t)sub >> lg; it < n_mtiles; it += item_step) {
                 const uint32_t su = it >> a.mt_log2, mi = it & (uint32_t)(a.mt - 1);
                 const TileCoord tc_ = decode_supertile((int)(blockIdx.x + su * gridDim.x), a);
@@ -522,7 +552,19 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                     am0 = __ldg(reinterpret_cast<const uint4 *>(ap + half));
                     am1 = __ldg(reinterpret_cast<const uint4 *>(ap + half) + 1);
                 }
-                if (inside) {
+                const uint32_t kn = kb + 1 == TC_NBUF ? 0u : kb + 1;
+                if (tma_out) {
+                    if (lane == 0) {
+                        bulk_wait_group_read<1>();      // only the previous item's store may still be reading: buffers kb and kn are free
+                        const uint32_t itn = it + item_step;
+                        if (has_res && itn < n_mtiles) {
+                            const TileCoord tn = decode_supertile((int)(blockIdx.x + (itn >> a.mt_log2) * gridDim.x), a);
+                            mbar_arrive_expect_tx(rfull0 + 8 * kn, TC_STAGE_BYTES);
+                            tma_load_4d(&tm.r, rfull0 + 8 * kn, sbuf0 + kn * TC_STAGE_BYTES, co,
+                                        (tn.tx + (int)(itn & (uint32_t)(a.mt - 1))) * TC_TW, tn.ty * TC_TH + q * 4, tn.b);
+                        }
+                    }
+                } else if (inside) {
                     if (has_res) {
                         rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
                         rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
@@ -564,7 +606,33 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
                 }
-                if (inside) {
+                if (tma_out) {
+                    const uint32_t sb = sbuf0 + kb * TC_STAGE_BYTES + lane_off;
+                    if (has_res) {
+                        mbar_wait(rfull0 + 8 * kb, kph);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rs0.x), "=r"(rs0.y), "=r"(rs0.z), "=r"(rs0.w) : "r"(sb + sw));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rs1.x), "=r"(rs1.y), "=r"(rs1.z), "=r"(rs1.w) : "r"(sb + (sw ^ 16u)));
+                        const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            yv[2 * j] += __uint_as_float(rr[j] << 16);
+                            yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = cvt_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + sw), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (sw ^ 16u)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (!TC_DBG(a, 8)) tma_store_4d(&tm.o, sbuf0 + kb * TC_STAGE_BYTES, co, (tc_.tx + (int)mi) * TC_TW, tc_.ty * TC_TH + q * 4, b);
+                        bulk_commit_group();
+                    }
+                    kb = kn;
+                    if (kb == 0) kph ^= 1u;
+                } else if (inside) {
                     if (has_res) {
                         const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
 #pragma unroll
@@ -597,6 +665,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
                 acc += item_step;
                 while (acc >= (uint32_t)a.nacc) { acc -= (uint32_t)a.nacc; acc_ph ^= 1u; }
             }
+            if (tma_out && lane == 0) bulk_wait_group<0>();      // staging buffers read and stores performed before the CTA retires
         } else
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x)
         for (int mi = 0; mi < a.mt; ++mi) {                           // the M tiles of the supertile, one accumulator slot each
@@ -811,6 +880,8 @@ struct TcGeom {
 //   tc_merge_done 1: ONE tcgen05.commit per tile for resident-weight, single-K-chunk layers (C=32: 87 -> 79 us, 97 -> 87 us)
 //   tc_commit_late / tc_bpair: fewer commits for supertiles / streamed weights - no gain, off
 int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0, g_tc_probe = 0;
+extern int g_tc_tma_store;   // conv_tc2.cu
+int g_tc_pair_wide = 1;   // ... and its streamed-weight variant for the Cin, Cout = 128 / 256 layers ("tc_pair_wide")
 int g_tc_pair = 1;        // CTA-pair (cta_group::2) kernel, conv_tc2.cu (read_set_option "tc_pair"): 0 = off, 1 = Cin 64 layers, 2 = every eligible layer
 int g_tc_mt = 1;          // supertile width (read_set_option "tc_mt"): 1 = plain 8x16 tiles (default: measured fastest), 0 = auto-widen, 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
@@ -941,7 +1012,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
     // measured ABAB at C3 (profiles/r02_conv_experiments.md): the pair kernel takes the C=64 layers from 73 to 56-68 us, but the C=32
     // layers (HBM-bound at 3-4.5 TB/s, they live on bytes in flight, not on tensor cycles) from 86 to 97 us -> pairs for Cin 64 only
-    if (g_tc_pair && tc2_supported(d) && d.out_mode == READ_OUT_NHWC && (d.Cin == 64 || g_tc_pair >= 2)) {
+    if (g_tc_pair && tc2_supported(d) && d.out_mode == READ_OUT_NHWC && (d.Cin == 64 || (d.Cin > 64 && g_tc_pair_wide) || g_tc_pair >= 2)) {
         const int rc2 = tc2_plan_create(d, &p->pair);
         if (rc2 != READ_OK) { delete p; return rc2; }
     }
@@ -1042,22 +1113,65 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.b_bytes = (uint32_t)g.n_tile * g.cin_blk * 2u;
     const uint32_t total_b = (uint32_t)(d.k * d.k * g.kchunks) * a.b_bytes;
     a.b_resident = (g.n_tiles == 1 && total_b <= TC_RESIDENT_MAX && TC_SMEM_BUDGET - total_b >= 2 * a.a_bytes) ? 1 : 0;
+    // Lean-epilogue layers (Cout 16 / 32 / 64, NHWC bf16 output, no second output) stage their output items for TMA stores when
+    // reserving the staging buffers does not cost them ring depth that matters (>= 6 stages or as many as without).
+    uint32_t budget = TC_SMEM_BUDGET;
+    a.tma_out = 0;
+    a.stage_bytes = 0;
+    {
+        const int half_n = g.n_tile >> 1;
+        const bool lean = (half_n == 16 || half_n == 32 || half_n == 64) && g.n_tiles == 1 && d.Cout == g.cout_pad &&
+                          (long long)d.B * d.Hout * d.Wout * d.Cout < (1ll << 31);
+        if (g_tc_tma_store && lean && d.out_mode == READ_OUT_NHWC && d.out2 == nullptr && budget > TC_STAGING_BYTES) {
+            const uint32_t small = budget - TC_STAGING_BYTES;
+            bool ok;
+            if (a.b_resident) {
+                const uint32_t full_st = (budget - total_b) / a.a_bytes, st = small > total_b ? (small - total_b) / a.a_bytes : 0;
+                ok = st >= 2 && (st >= 6 || st >= full_st || st >= (uint32_t)TC_MAX_STAGES);
+            } else {
+                const uint32_t full_st = (budget - 3 * a.a_bytes) / a.b_bytes, st = small > 3 * a.a_bytes ? (small - 3 * a.a_bytes) / a.b_bytes : 0;
+                ok = st >= 2 && (st >= 6 || st >= full_st || st >= (uint32_t)TC_MAX_STAGES);
+            }
+            if (ok) {
+                a.tma_out = 1;
+                a.stage_bytes = TC_STAGING_BYTES;
+                budget = small;
+            }
+        }
+    }
     uint32_t b_region_bytes;
     if (a.b_resident) {
-        int st = (int)((TC_SMEM_BUDGET - total_b) / a.a_bytes);
+        int st = (int)((budget - total_b) / a.a_bytes);
         a.a_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         a.b_stages = 0;
         b_region_bytes = total_b;
     } else {
         a.a_stages = 3;
-        if (3 * a.a_bytes + 2 * a.b_bytes > TC_SMEM_BUDGET) {
+        if (3 * a.a_bytes + 2 * a.b_bytes > budget) {
             set_error("tcgen05 conv: layer does not fit shared memory (A stage %u B, B tile %u B)", a.a_bytes, a.b_bytes);
             delete p;
             return READ_ERR_UNSUPPORTED;
         }
-        int st = (int)((TC_SMEM_BUDGET - 3 * a.a_bytes) / a.b_bytes);
+        int st = (int)((budget - 3 * a.a_bytes) / a.b_bytes);
         a.b_stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         b_region_bytes = (uint32_t)a.b_stages * a.b_bytes;
+    }
+    if (a.tma_out) {   // epilogue items: 16 channels x 8 x 4 pixels of the NHWC output (store) / residual (load), 32-byte swizzle
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.Wout, (cuuint64_t)d.Hout, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)d.Wout * d.Cout * 2, (cuuint64_t)d.Hout * d.Wout * d.Cout * 2};
+        cuuint32_t box[4] = {16, (cuuint32_t)TC_TW, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p->tmA.o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = enc(&p->tmA.r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.residual ? const_cast<void *>(d.residual) : d.out, dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tcgen05 conv: cuTensorMapEncodeTiled(output items) failed with %d", (int)r);
+            delete p;
+            return READ_ERR_CUDA;
+        }
     }
     a.inv_tx = 1.0f / (float)a.tiles_x;
     a.inv_ty = 1.0f / (float)a.tiles_y;
@@ -1094,7 +1208,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     a.addin = static_cast<const __nv_bfloat16 *>(d.addin);
     a.addin_H = d.addin_H; a.addin_W = d.addin_W;
     a.raw = d.out_mode == READ_OUT_RAW_NHWC ? 1 : 0;
-    p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + 8 * BAR_PARAMS + 16 * (size_t)g.cout_pad + 64;
+    p->smem_bytes = 1024 + (size_t)a.b_region_off + b_region_bytes + a.stage_bytes + 8 * BAR_PARAMS + 16 * (size_t)g.cout_pad + 64;
     *out = p;
     return READ_OK;
 }

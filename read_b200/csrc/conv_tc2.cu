@@ -57,7 +57,8 @@ struct Tc2Args {
     int tiles_x, tiles_y;
     long long n_tiles;                        // M tiles of the layer
     float inv_tx, inv_ty;
-    int slots;                                // A ring depth == accumulator ring depth
+    int slots;                                // A ring depth == accumulator ring depth (resident weights)
+    int kchunks, nn_log2, a_stages, b_stages; // streamed weights: K chunks of 64 channels, log2(n tiles), ring depths
     int halo_w;
     uint32_t a_tx_bytes, a_bytes;             // halo tile bytes, rounded to 1 KB
     uint32_t b_half_bytes;                    // one tap's half weight tile: (n_tile / 2) x cin_blk bf16
@@ -423,6 +424,252 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------ streamed-weight variant (Cin, Cout = 128 / 256)
+// The wide ResBlock layers do not fit their weights in shared memory: the single-CTA kernel streams one [n_tile x 64] weight tile
+// (32 KB) per tap and K chunk for every 128-pixel tile, ~590 KB per tile, 600 MB per layer - at the layer's 66 us that is 9 TB/s out
+// of L2, i.e. the layer is L2-bandwidth bound, not tensor bound (72 MMAs x 128 cycles per tile would be 38 us).  As a CTA pair
+// (M = 256) each CTA streams only ITS half of the weight rows (CTA 0: conv_f rows, CTA 1: conv_m rows of the n tile), halving the
+// L2 -> SM traffic per pixel.  Work unit = (tile pair, n tile); rings: A = one halo tile per (unit, K chunk), B = one half weight
+// tile per (unit, K chunk, tap); accumulators: 2 x 256 TMEM columns.
+//   afull / bfull (leader's): both CTAs' TMA loads complete_tx on the leader's barrier
+//   aempty / bempty / tfull (each CTA's own): tcgen05.commit multicast
+//   tempty (leader's): every epilogue warp of both CTAs arrives after its last TMEM load of the unit
+constexpr int S2_AFULL = 0, S2_AEMPTY = 4, S2_BFULL = 8, S2_BEMPTY = 24, S2_TFULL = 40, S2_TEMPTY = 42, S2_TMEMPTR = 44, S2_PARAMS = 46;
+constexpr int S2_MAX_A = 4, S2_MAX_B = 16;
+
+template <int KS, int KKN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
+gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Tc2Args a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (s_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
+    constexpr int ntaps = KS * KS;
+    const uint32_t b_region = smem_base + a.b_region_off;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + (uint32_t)a.b_stages * a.b_half_bytes);
+    const uint32_t bar0 = s_u32(bars);
+    const uint32_t afull0 = bar0 + 8 * S2_AFULL, aempty0 = bar0 + 8 * S2_AEMPTY, bfull0 = bar0 + 8 * S2_BFULL, bempty0 = bar0 + 8 * S2_BEMPTY;
+    const uint32_t tfull0 = bar0 + 8 * S2_TFULL, tempty0 = bar0 + 8 * S2_TEMPTY;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + S2_TMEMPTR);
+    float *s_par = reinterpret_cast<float *>(bars + S2_PARAMS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (a.pdl) pdl_launch_dependents();
+
+    for (int i = threadIdx.x; i < a.Cout; i += 640)        // {bias_f, bias_m, bn_scale, bn_shift}: gate_fast, as the single-CTA wide epilogue
+        reinterpret_cast<float4 *>(s_par)[i] = make_float4(a.bias_f[i], a.bias_m[i], a.scale[i], a.shift[i]);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S2_MAX_A; ++s) {
+            mbar_init(afull0 + 8 * s, 1);
+            mbar_init(aempty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < S2_MAX_B; ++s) {
+            mbar_init(bfull0 + 8 * s, 1);
+            mbar_init(bempty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, 32);                  // 16 epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc2(s_u32(tmem_ptr_smem), T2_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const uint32_t n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int nn_log2 = a.nn_log2;                           // n tiles per pixel tile: 1 or 2
+    const long long n_units = ((a.n_tiles + 1) >> 1) << nn_log2;
+    const uint32_t my_units = n_units > cluster_id ? (uint32_t)((n_units - cluster_id + n_clusters - 1) / n_clusters) : 0u;
+    const int half = a.n_tile >> 1;
+    const int n_total = a.n_tile << nn_log2;
+    const uint32_t a_stages = (uint32_t)a.a_stages, b_stages = (uint32_t)a.b_stages;
+    const int kchunks = a.kchunks;
+    // unit i of this cluster -> (tile of this CTA, n tile)
+    auto unit_tile = [&](uint32_t i, int &nt) -> long long {
+        const long long u = (long long)cluster_id + (long long)i * n_clusters;
+        nt = (int)(u & ((1 << nn_log2) - 1));
+        return 2ll * (u >> nn_log2) + rank;
+    };
+
+    if (warp == 0) {
+        // ===================== A producer: one halo tile per (unit, K chunk) =====================
+        if (a.pdl) pdl_wait();
+        uint32_t as = 0, aph = 0;
+        for (uint32_t i = 0; i < my_units; ++i) {
+            int nt;
+            const long long t = unit_tile(i, nt);
+            const Tile2 tc = decode2((int)t, a);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(afull0 + 8 * as, 2u * a.a_tx_bytes);
+                    tma2_load_4d(&tmA, (afull0 + 8 * as) & PEER_MASK, smem_base + as * a.a_bytes, kc * (KKN * 16), tc.tx * T2_TW - a.pad,
+                                 tc.ty * T2_TH - a.pad, tc.b);
+                }
+                __syncwarp();
+                if (++as == a_stages) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== B producer: this CTA's half of the weight rows, one tile per (unit, K chunk, tap) =====================
+        uint32_t bs = 0, bph = 0;
+        for (uint32_t i = 0; i < my_units; ++i) {
+            int nt;
+            (void)unit_tile(i, nt);
+            const int row0 = nt * a.n_tile + (int)rank * half;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+                    if (elect_one()) {
+                        if (leader) mbar_arrive_expect_tx(bfull0 + 8 * bs, 2u * a.b_half_bytes);
+                        tma2_load_2d(&tmB, (bfull0 + 8 * bs) & PEER_MASK, b_region + bs * a.b_half_bytes, 0, (tap * kchunks + kc) * n_total + row0);
+                    }
+                    __syncwarp();
+                    if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((256u >> 4) << 24);
+            constexpr uint32_t row_bytes = KKN * 16u * 2u;
+            constexpr uint32_t layout_type = (KKN == 4) ? 2u : 4u;
+            const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, (uint32_t)a.halo_w * row_bytes, layout_type) >> 32);
+            const uint32_t desc_hi_b = (uint32_t)(make_kmajor_desc(0, 8u * row_bytes, layout_type) >> 32);
+            constexpr uint32_t lo_lbo = 1u << 16;
+            constexpr uint32_t px16 = row_bytes >> 4;
+            const uint32_t ky_step = (uint32_t)a.halo_w * px16;
+            const uint32_t a16 = a.a_bytes >> 4, b16 = a.b_half_bytes >> 4;
+            const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | lo_lbo, b_lo0 = ((b_region & 0x3FFFFu) >> 4) | lo_lbo;
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, acc_ph = 0;
+            for (uint32_t i = 0; i < my_units; ++i) {
+                mbar_wait(tempty0 + 8 * acc, acc_ph ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_tile;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(afull0 + 8 * as, aph);
+                    tcgen05_fence_after();
+                    const uint32_t a_lo = a_lo0 + as * a16;
+#pragma unroll
+                    for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx) {
+                            mbar_wait(bfull0 + 8 * bs, bph);
+                            tcgen05_fence_after();
+                            if (elect_one()) {
+                                const uint32_t bl = b_lo0 + bs * b16;
+                                const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
+#pragma unroll
+                                for (int kk = 0; kk < KKN; ++kk)
+                                    umma2_bf16(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, (kc | ky | kx | kk) != 0 ? 1u : 0u);
+                                umma2_commit_multicast(bempty0 + 8 * bs);
+                            }
+                            __syncwarp();
+                            if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                    if (elect_one()) {
+                        umma2_commit_multicast(aempty0 + 8 * as);
+                        if (kc == kchunks - 1) umma2_commit_multicast(tfull0 + 8 * acc);
+                    }
+                    __syncwarp();
+                    if (++as == a_stages) { as = 0; aph ^= 1u; }
+                }
+                if (++acc == 2u) { acc = 0; acc_ph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 16 warps, warp (q, sub) owns the 16-channel chunks sub, sub + 4, .. of its 32 pixels =====================
+        const int q = warp & 3;
+        const int sub = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int py = r / T2_TW, px = r % T2_TW;
+        const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
+        const int nch16 = half >> 4;
+        if (a.pdl) pdl_wait();
+        uint32_t acc = 0, acc_ph = 0;
+        for (uint32_t i = 0; i < my_units; ++i) {
+            int nt;
+            const long long t = unit_tile(i, nt);
+            const Tile2 tc = decode2((int)t, a);
+            const int x = tc.tx * T2_TW + px, y = tc.ty * T2_TH + py;
+            const bool inside = (t < a.n_tiles) && (x < a.W) && (y < a.H);
+            const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
+            const int o0 = ((tc.b * a.H + y) * a.W + x) * a.Cout + nt * half;
+            mbar_wait(tfull0 + 8 * acc, acc_ph);
+            tcgen05_fence_after();
+            for (int c = sub; c < nch16; c += 4) {
+                const int o = o0 + c * 16;
+                uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0;
+                if (inside && a.residual != nullptr) {
+                    rs0 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o));
+                    rs1 = __ldg(reinterpret_cast<const uint4 *>(a.residual + o) + 1);
+                }
+                uint32_t f16[16], m16[16];
+                tmem_ld16(trow + (uint32_t)(c * 16), f16);
+                tmem_ld16(trow + (uint32_t)(half + c * 16), m16);
+                tmem_ld_wait();
+                if (c + 4 >= nch16) {          // last chunk of this warp: the accumulator slot goes back to the issuer before the math
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster((tempty0 + 8 * acc) & PEER_MASK);
+                }
+                const int co = nt * half + c * 16;
+                float yv[16];
+                if (a.elu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 pp = par4[co + j];
+                        yv[j] = gate_fast<true>(__uint_as_float(f16[j]) + pp.x, __uint_as_float(m16[j]) + pp.y, pp.z, pp.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 pp = par4[co + j];
+                        yv[j] = gate_fast<false>(__uint_as_float(f16[j]) + pp.x, __uint_as_float(m16[j]) + pp.y, pp.z, pp.w);
+                    }
+                }
+                if (inside) {
+                    if (a.residual != nullptr) {
+                        const uint32_t rr[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            yv[2 * j] += __uint_as_float(rr[j] << 16);
+                            yv[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = cvt2_bf16x2(yv[2 * j], yv[2 * j + 1]);
+                    uint4 *op = reinterpret_cast<uint4 *>(a.out + o);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            if (++acc == 2u) { acc = 0; acc_ph ^= 1u; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc2(tmem_base, T2_TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -433,15 +680,18 @@ struct Tc2Plan {
     CUtensorMap tmA, tmB, tmO, tmR;
     Tc2Args args;
     size_t smem_bytes;
-    int kkn, epi;
+    int kkn, epi, wide;
 };
 
 bool tc2_supported(const read_conv_desc &d)
 {
     if (d.act_dtype != READ_ACT_BF16 || d.mul != nullptr || d.n_src != 1 || d.src[0].mode != READ_SRC_IDENTITY) return false;
     if (d.stride != 1 || d.k != 3 || d.pad != 1 || d.Hin != d.Hout || d.Win != d.Wout) return false;
-    if (!(d.Cin == 32 || d.Cin == 64)) return false;                       // one K chunk
-    if (!(d.Cout == 16 || d.Cout == 32 || d.Cout == 64)) return false;
+    const bool wide = (d.Cin == 128 || d.Cin == 256) && (d.Cout == 128 || d.Cout == 256);     // streamed weights, 256-column n tiles
+    if (!wide) {
+        if (!(d.Cin == 32 || d.Cin == 64)) return false;                       // one K chunk, resident weights
+        if (!(d.Cout == 16 || d.Cout == 32 || d.Cout == 64)) return false;
+    }
     if (d.out_mode != READ_OUT_NHWC || d.out2 != nullptr || d.addin != nullptr) return false;
     if ((long long)d.B * d.Hout * d.Wout * d.Cout >= (1ll << 31)) return false;
     return true;
@@ -460,7 +710,8 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     }
     Tc2Plan *p = new (std::nothrow) Tc2Plan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 pair conv: out of host memory");
-    const int cin_blk = d.Cin, n_tile = 2 * d.Cout;
+    const bool wide = d.Cin > 64;
+    const int cin_blk = wide ? 64 : d.Cin, n_tile = wide ? 256 : 2 * d.Cout;
     const int halo_rows = T2_TH + d.k - 1, halo_w = T2_TW + d.k - 1;
     const CUtensorMapSwizzle sw = cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
@@ -478,7 +729,7 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
         }
     }
     {   // weights packed as for conv_tc ([tap][n][cin_blk], conv_f rows then conv_m rows): box = HALF the N rows of one tap
-        const cuuint64_t rows = (cuuint64_t)d.k * d.k * n_tile;
+        const cuuint64_t rows = (cuuint64_t)d.k * d.k * (d.Cin / cin_blk) * 2 * d.Cout;
         cuuint64_t dims[2] = {(cuuint64_t)cin_blk, rows};
         cuuint64_t strides[1] = {(cuuint64_t)cin_blk * 2};
         cuuint32_t box[2] = {(cuuint32_t)cin_blk, (cuuint32_t)(n_tile / 2)};
@@ -491,7 +742,7 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
             return READ_ERR_CUDA;
         }
     }
-    {   // epilogue items: 16 channels x 8 x 4 pixels of the NHWC output (store) / of the residual tensor (load), 32-byte swizzle
+    if (!wide) {   // epilogue items: 16 channels x 8 x 4 pixels of the NHWC output (store) / of the residual tensor (load), 32-byte swizzle
         cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.Wout, (cuuint64_t)d.Hout, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)d.Wout * d.Cout * 2, (cuuint64_t)d.Hout * d.Wout * d.Cout * 2};
         cuuint32_t box[4] = {16, (cuuint32_t)T2_TW, 4, 1};
@@ -520,6 +771,33 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     a.a_tx_bytes = (uint32_t)halo_rows * halo_w * cin_blk * 2u;
     a.a_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
     a.b_half_bytes = (uint32_t)(n_tile / 2) * cin_blk * 2u;
+    a.kchunks = d.Cin / cin_blk;
+    a.nn_log2 = (2 * d.Cout) / n_tile == 2 ? 1 : 0;
+    a.elu = d.elu;
+    a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
+    a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
+    a.out = static_cast<__nv_bfloat16 *>(d.out);
+    p->kkn = cin_blk / 16;
+    p->wide = wide ? 1 : 0;
+    if (wide) {
+        a.slots = 2;
+        a.a_stages = 3;
+        const size_t fixed = 1024 + 8 * S2_PARAMS + 16 * (size_t)d.Cout + 64;
+        size_t left = 227 * 1024 - fixed - (size_t)a.a_stages * a.a_bytes;
+        a.b_stages = (int)(left / a.b_half_bytes);
+        if (a.b_stages > S2_MAX_B) a.b_stages = S2_MAX_B;
+        if (a.b_stages < 4) {
+            set_error("tcgen05 pair conv: layer does not fit shared memory");
+            delete p;
+            return READ_ERR_UNSUPPORTED;
+        }
+        a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
+        a.stage_off = 0;
+        p->smem_bytes = fixed + (size_t)a.a_stages * a.a_bytes + (size_t)a.b_stages * a.b_half_bytes;
+        p->epi = 0;
+        *out = p;
+        return READ_OK;
+    }
     const int nacc = T2_TMEM_COLS / n_tile > T2_MAX_SLOTS ? T2_MAX_SLOTS : T2_TMEM_COLS / n_tile;
     a.slots = nacc;
     {   // the A ring (one halo tile per accumulator slot) shares 227 KB with the resident weights and the epilogue's staging buffers
@@ -528,12 +806,7 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     }
     a.b_region_off = (uint32_t)a.slots * a.a_bytes;
     a.stage_off = a.b_region_off + (uint32_t)(d.k * d.k) * a.b_half_bytes;          // a multiple of 1 KB (b_half_bytes is)
-    a.elu = d.elu;
-    a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
-    a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
-    a.out = static_cast<__nv_bfloat16 *>(d.out);
     p->smem_bytes = 1024 + (size_t)a.stage_off + 16 * T2_NBUF * T2_STAGE_BYTES + 8 * B2_PARAMS + 16 * (size_t)d.Cout + 64;
-    p->kkn = cin_blk / 16;
     p->epi = (a.elu && !a.residual) ? 1 : ((!a.elu && a.residual) ? 2 : 0);
     if (p->smem_bytes > 227 * 1024) {
         set_error("tcgen05 pair conv: layer does not fit shared memory");
@@ -558,7 +831,7 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
     a.tma_out = g_tc_tma_store ? 1 : 0;
     if (a.n_tiles == 0) return READ_OK;
     long long grid = num_sms() & ~1;                  // whole pairs
-    const long long units = (a.n_tiles + 1) / 2;
+    const long long units = ((a.n_tiles + 1) / 2) << (p->wide ? a.nn_log2 : 0);
     if (grid > 2 * units) grid = 2 * units;
     cudaLaunchAttribute lattr[1];            // the cluster shape (2,1,1) is a compile-time attribute of the kernel
     lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -570,6 +843,12 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
     lcfg.stream = st;
     lcfg.attrs = lattr;
     lcfg.numAttrs = a.pdl ? 1 : 0;
+    if (p->wide) {
+        RB_CUDA(cudaFuncSetAttribute(gated_conv_tc2s_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+        RB_CUDA(cudaLaunchKernelEx(&lcfg, gated_conv_tc2s_kernel<3, 4>, p->tmA, p->tmB, a));
+        RB_LAUNCH_CHECK();
+        return READ_OK;
+    }
 #define RB_TC2(KKN_, EPI_)                                                                                              \
     do {                                                                                                                \
         RB_CUDA(cudaFuncSetAttribute(gated_conv_tc2_kernel<3, KKN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

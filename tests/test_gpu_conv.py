@@ -386,12 +386,22 @@ PAIR_CASES = [
     ("C64 -> 32 channels, no activation", [(64, 20, 24, "id", 1)], 32, 3, False, {}),
     ("persistent C32, 2560 tiles (17 pairs per cluster: rings wrap)", [(32, 512, 640, "id", 1)], 32, 3, True, {"residual": True}),
     ("persistent C64 + residual, 1280 tiles", [(64, 256, 640, "id", 1)], 64, 3, False, {"residual": True}),
+    # streamed-weight variant (conv_tc2.cu gated_conv_tc2s_kernel): K chunks of 64 channels, 256-column n tiles
+    ("wide C128 24x40 (2 K chunks)", [(128, 24, 40, "id", 1)], 128, 3, True, {}),
+    ("wide C128 ragged, odd tile count + residual", [(128, 19, 23, "id", 1)], 128, 3, False, {"residual": True}),
+    ("wide C256 (4 K chunks, 2 n tiles)", [(256, 17, 24, "id", 1)], 256, 3, True, {}),
+    ("wide C256 + residual, one tile per image", [(256, 16, 8, "id", 1)], 256, 3, False, {"residual": True}),
+    ("wide C128 -> 256", [(128, 16, 16, "id", 1)], 256, 3, True, {}),
+    ("wide C256 -> 128", [(256, 16, 24, "id", 1)], 128, 3, True, {}),
+    ("persistent wide C128, 1360 tiles (rings wrap many times)", [(128, 272, 640, "id", 1)], 128, 3, False, {"residual": True}),
+    ("persistent wide C256, 680 tiles x 2 n tiles", [(256, 136, 640, "id", 1)], 256, 3, True, {}),
 ]
 
 
 @pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
 def test_tcgen05_cta_pair_matches_torch_and_the_single_cta_kernel(case):
-    """cta_group::2 variant: same tolerance as the single-CTA kernel against torch, and bit-identical to it (same K order)."""
+    """cta_group::2 variant: same tolerance as the single-CTA kernel against torch; the resident-weight kernel is bit-identical to
+    it (same K order), the streamed-weight one accumulates the taps in a different order (within one bf16 ulp of it)."""
     lib = L.load()
     _, srcs, cout, k, elu, kw = case
     try:
@@ -404,4 +414,7 @@ def test_tcgen05_cta_pair_matches_torch_and_the_single_cta_kernel(case):
     assert torch.isfinite(got).all(), "pair kernel left outputs unwritten (NaN sentinel)"
     tol = 2 ** -8 * float(want.abs().max()) + 4e-3
     assert float((got - want).abs().max()) < tol
-    assert torch.equal(got, base)
+    if case[0].startswith(("wide", "persistent wide")):
+        assert float((got - base).abs().max()) <= 2 ** -7 * float(want.abs().max())
+    else:
+        assert torch.equal(got, base)
