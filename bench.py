@@ -303,6 +303,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L.require_device(local)
     lib = L.load()
+    if args.profile_timed_region and os.environ.get("READ_BENCH_PROFILE_PDL", "0") == "0":
+        # ncu's graph-node profiling failed (LaunchFailed) on graphs with programmatic-dependency edges: the launch list is taken
+        # with plain stream order (kernel durations are unaffected; ncu serialises the launches anyway)
+        L.check(lib.read_set_option(b"tc_pdl", 0))
     pk = peaks()
 
     # ---- scene state (loaded once, like MyRender.update_ds / load_textures): resident in HBM.  The public plugin object owns it.
@@ -321,6 +325,8 @@ def run_ours(args):
         fr.xyz = None
         torch.cuda.empty_cache()
     B = world                                   # views per step
+    if args.profile_timed_region and os.environ.get("READ_BENCH_NO_GRAPH") == "1":
+        net.use_graph = False                   # profiling aid: eager replay of the same launches
     eng = net.engine(1, H, W, dev)              # each rank refines ONE view per step
     tex_nd = tex.point_major()
     layout = L.FEAT_NHWC_BF16 if eng.bf16 else L.FEAT_NHWC_F32
@@ -403,6 +409,17 @@ def run_ours(args):
         resident_step(s)
     torch.cuda.synchronize()
     launches_per_step = (2 + eng.n_launches()) if world == 1 else (4 + eng.n_launches())
+    if args.profile_timed_region:
+        # ncu --profile-from-start off: the capture holds exactly the launches of the timed steps (the launch list under profiles/);
+        # numbers printed by such a run are not bench values, so nothing else is measured
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        ms_p = timed(resident_step, args.steps, args.warmup)
+        torch.cuda.cudart().cudaProfilerStop()
+        if rank == 0:
+            print(json.dumps({"profiled_steps": args.steps, "launches_per_step": launches_per_step, "ms_under_profiler": ms_p,
+                              "note": "profiling run: not a bench value"}))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
@@ -429,6 +446,7 @@ def run_ours(args):
     sp = L.stream_ptr()
     L.check(lib.read_set_option(b"tc_pdl", 0))
     tc_ms = tc_flops = gen_ms = gen_flops = tcg_ms = tcg_flops = tco_ms = tco_flops = 0.0
+    tc_classes = {}
     layer_rows = []
     aux_ms = 0.0
     for ly in eng.ops:
@@ -441,6 +459,9 @@ def run_ours(args):
                            "tflops": ly.flops / (t * 1e-3) / 1e12})
         if ly.impl == L.CONV_TCGEN05 and ly.k == 3 and ly.stride == 1:
             tc_ms += t; tc_flops += ly.flops          # the tensor-bound instances: 3x3 stride-1 C->C convs
+            if getattr(ly, "cin", None) == getattr(ly, "cout", -1) and ly.cin in (32, 64, 128, 256):
+                c_ = tc_classes.setdefault(f"C{ly.cin}", [0, 0.0, 0.0])
+                c_[0] += 1; c_[1] += t; c_[2] += ly.flops
         elif ly.impl == L.CONV_TCGEN05:
             tco_ms += t; tco_flops += ly.flops        # 1x1 / stride-2 / RAW-term launches: HBM- and latency-bound
         elif ly.impl == L.CONV_TCGEN05_GATHER:
@@ -488,8 +509,12 @@ def run_ours(args):
     traf = measured_traffic()
     if tc_ms > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
-        roof_tc = {"kernel": "gated_conv_tc_kernel<3,*,*,*,*,1> (tcgen05 implicit-GEMM gated conv, 3x3 stride-1 instances = "
-                             f"{100.0 * tc_flops / max(eng.flops, 1):.1f}% of the net's conv FLOPs)", "bound": "tensor",
+        kern = {"C32": "gated_conv_tc_kernel (one CTA, resident weights)", "C64": "gated_conv_tc2_kernel (CTA pair, resident weights)",
+                "C128": "gated_conv_tc2s_kernel (CTA pair, streamed weights)", "C256": "gated_conv_tc2s_kernel (CTA pair, streamed weights)"}
+        roof_tc = {"kernel": "tcgen05 implicit-GEMM gated conv, 3x3 stride-1 instances (gated_conv_tc_kernel / gated_conv_tc2_kernel / "
+                             f"gated_conv_tc2s_kernel) = {100.0 * tc_flops / max(eng.flops, 1):.1f}% of the net's conv FLOPs", "bound": "tensor",
+                   "by_class": {k_: {"layers": v_[0], "us_per_layer": 1e3 * v_[1] / v_[0], "tflops": v_[2] / (v_[1] * 1e-3) / 1e12,
+                                     "frac": v_[2] / (v_[1] * 1e-3) / 1e12 / tens_peak, "kernel": kern[k_]} for k_, v_ in tc_classes.items()},
                    "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
                    "peak_src": pk["src"] + " bf16_tflops (burst: each launch timed alone)",
                    "frac_of_sustained": ach / pk["bf16_tflops_sustained"],
@@ -803,6 +828,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--profile-timed-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps and exit (for ncu --profile-from-start off)")
     ap.add_argument("--layer-times", default=None, help="write per-layer CUDA-event timings (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -128,6 +128,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # READ_B200_OPTIONS="name=value,name=value": tuning options (read_set_option) applied at load time
+    for item in filter(None, os.environ.get("READ_B200_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        if lib.read_set_option(name.strip().encode(), int(value)) != 0:
+            raise RuntimeError(f"read_b200: READ_B200_OPTIONS: unknown option {name!r}")
     return lib
 
 

@@ -15,7 +15,7 @@ _MODE = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_U
 
 
 class _Layer:
-    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride", "kind")
+    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride", "kind", "cin", "cout")
 
 
 class UNetEngine:
@@ -156,6 +156,7 @@ class UNetEngine:
         ly.name, ly.plan, ly.impl, ly.keep = (name or prefix), plan, lib.read_conv_plan_impl(plan), keep
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
         ly.k, ly.stride, ly.kind = k, stride, "conv"
+        ly.cin, ly.cout = cin, cout
         self.layers.append(ly)
         self.ops.append(ly)
         self._after_conv(srcs, k, stride, out, out2, residual, out2_mul, addin, final)
