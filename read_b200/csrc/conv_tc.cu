@@ -241,7 +241,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         }
         for (int i = 0; i < TC_MAX_ACC; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, NTHR == 640 ? (a.raw ? 16u : (uint32_t)(a.n_tile >> 3)) : (NTHR - 128) / 32);   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
+            mbar_init(tempty0 + 8 * i, NTHR == 640 ? (a.raw ? 16u : (uint32_t)(a.n_tile >> 3)) : ((a.n_tile >> 1) == 8 ? 4u : (NTHR - 128) / 32));   // arrivals per tile: lean = 4 quadrants x nch16 warps, else every epilogue warp
         }
         mbar_init(bres, 1);
         if (NTHR == 640)
@@ -491,6 +491,7 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
         const int half = a.n_tile >> 1;
         const int nchunks = half >> 4;
         const float4 *par4 = reinterpret_cast<const float4 *>(s_par);
+        unsigned tile_seq = 0;                      // this CTA's tile counter (final layer: tiles alternate between the quadrant's two warps)
         uint32_t acc_c = 0, acc_p = 0;
         if (a.pdl) pdl_wait();        // residual / add-in / FAM-multiplier tensors come from earlier kernels
         if (NTHR == 640 && (EPI != 0 || !a.raw)) {
@@ -679,10 +680,14 @@ gated_conv_tc_kernel(const __grid_constant__ TcMaps tm, const __grid_constant__ 
             const uint32_t trow = tmem_base + acc * (uint32_t)a.n_tile + ((uint32_t)(q * 32) << 16);
 
             if (half == 8) {
-                // final layer (unet.py:285: BasicConv(32 -> 3), Cout padded to 8): one 8-column chunk, NCHW fp32 output
+                // final layer (unet.py:285: BasicConv(32 -> 3), Cout padded to 8): one 8-column chunk, NCHW fp32 output.
+                // The two warps of a TMEM lane quadrant take ALTERNATE tiles (tempty counts 4 arrivals): a warp's wait / load / store
+                // chain is ~1400 cycles per tile and nothing else bounds this layer, so two chains in flight halve the tile period.
+                const bool mine = ((unsigned)tile_seq++ & 1u) == (unsigned)sub;
+                if (!mine) continue;
                 mbar_wait(tfull0 + 8 * acc, acc_ph);
                 tcgen05_fence_after();
-                if (sub == 0) {
+                {
                     uint32_t f8[8], m8[8];
                     tmem_ld8(trow, f8);
                     tmem_ld8(trow + 8u, m8);
@@ -882,7 +887,7 @@ struct TcGeom {
 int g_tc_commit_late = 0, g_tc_merge_done = 1, g_tc_bpair = 0, g_tc_probe = 0;
 extern int g_tc_tma_store;   // conv_tc2.cu
 int g_tc_pair_wide = 1;   // ... and its streamed-weight variant for the Cin, Cout = 128 / 256 layers ("tc_pair_wide")
-int g_tc_pair = 1;        // CTA-pair (cta_group::2) kernel, conv_tc2.cu (read_set_option "tc_pair"): 0 = off, 1 = Cin 64 layers, 2 = every eligible layer
+int g_tc_pair = 1;        // CTA-pair (cta_group::2) kernel, conv_tc2.cu (read_set_option "tc_pair"): 0 = off, 1 = Cin 64 layers and Cin 32 layers without a residual (measured ABAB: 81 -> 73 us; with a residual the pair is 2 us slower), 2 = every eligible layer
 int g_tc_mt = 1;          // supertile width (read_set_option "tc_mt"): 1 = plain 8x16 tiles (default: measured fastest), 0 = auto-widen, 2 / 4 = force where legal
 // K-chunk granularity of a layer: the widest block (64 or 32 channels) that divides EVERY source of a virtual concat
 static int desc_chan_gran(const read_conv_desc &d)
@@ -1012,7 +1017,7 @@ int tc_plan_create(const read_conv_desc &d, TcPlan **out)
     RB_CHECK_ARG(p != nullptr, "tcgen05 conv: out of host memory");
     // measured ABAB at C3 (profiles/r02_conv_experiments.md): the pair kernel takes the C=64 layers from 73 to 56-68 us, but the C=32
     // layers (HBM-bound at 3-4.5 TB/s, they live on bytes in flight, not on tensor cycles) from 86 to 97 us -> pairs for Cin 64 only
-    if (g_tc_pair && tc2_supported(d) && d.out_mode == READ_OUT_NHWC && (d.Cin == 64 || (d.Cin > 64 && g_tc_pair_wide) || g_tc_pair >= 2)) {
+    if (g_tc_pair && tc2_supported(d) && d.out_mode == READ_OUT_NHWC && (d.Cin == 64 || (d.Cin == 32 && d.residual == nullptr) || (d.Cin > 64 && g_tc_pair_wide) || g_tc_pair >= 2)) {
         const int rc2 = tc2_plan_create(d, &p->pair);
         if (rc2 != READ_OK) { delete p; return rc2; }
     }

@@ -430,11 +430,15 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // of L2, i.e. the layer is L2-bandwidth bound, not tensor bound (72 MMAs x 128 cycles per tile would be 38 us).  As a CTA pair
 // (M = 256) each CTA streams only ITS half of the weight rows (CTA 0: conv_f rows, CTA 1: conv_m rows of the n tile), halving the
 // L2 -> SM traffic per pixel.  Work unit = (tile pair, n tile); rings: A = one halo tile per (unit, K chunk), B = one half weight
-// tile per (unit, K chunk, tap); accumulators: 2 x 256 TMEM columns.
+// tile per (unit, K chunk, tap); accumulators: 512 / n_tile TMEM slots.  Unit width n_tile = 256 columns.  (Cout = 256 at C3: its
+// 1/8-size image has only 128 tile pairs -> 256 units of ~18 us over 74 clusters = 3.46 rounds of work in 4.  128-column units
+// ("tc_wide_ntile" 128: 512 half-size units, 7 rounds of 6.9) were measured SLOWER, 73 vs 66 us per layer: with four 64-cycle MMAs per
+// weight stage the issuing thread's per-stage wait + commit is no longer hidden.)  The weights stay in conv_tc's packing ([tap][K chunk]
+// [n tile of 256: 128 conv_f rows | 128 conv_m rows][64]): a unit's conv_f / conv_m rows are two row ranges of it.
 //   afull / bfull (leader's): both CTAs' TMA loads complete_tx on the leader's barrier
 //   aempty / bempty / tfull (each CTA's own): tcgen05.commit multicast
 //   tempty (leader's): every epilogue warp of both CTAs arrives after its last TMEM load of the unit
-constexpr int S2_AFULL = 0, S2_AEMPTY = 4, S2_BFULL = 8, S2_BEMPTY = 24, S2_TFULL = 40, S2_TEMPTY = 42, S2_TMEMPTR = 44, S2_PARAMS = 46;
+constexpr int S2_AFULL = 0, S2_AEMPTY = 4, S2_BFULL = 8, S2_BEMPTY = 24, S2_TFULL = 40, S2_TEMPTY = 44, S2_TMEMPTR = 48, S2_PARAMS = 50;
 constexpr int S2_MAX_A = 4, S2_MAX_B = 16;
 
 template <int KS, int KKN>
@@ -473,7 +477,7 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(bfull0 + 8 * s, 1);
             mbar_init(bempty0 + 8 * s, 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
             mbar_init(tempty0 + 8 * s, 32);                  // 16 epilogue warps of each CTA
         }
@@ -487,11 +491,12 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const uint32_t n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-    const int nn_log2 = a.nn_log2;                           // n tiles per pixel tile: 1 or 2
+    const int nn_log2 = a.nn_log2;                           // log2(units per tile pair) = log2(2 * Cout / n_tile): 0, 1 or 2
+    const uint32_t slots = (uint32_t)a.slots;                // accumulator ring: 512 / n_tile
     const long long n_units = ((a.n_tiles + 1) >> 1) << nn_log2;
     const uint32_t my_units = n_units > cluster_id ? (uint32_t)((n_units - cluster_id + n_clusters - 1) / n_clusters) : 0u;
     const int half = a.n_tile >> 1;
-    const int n_total = a.n_tile << nn_log2;
+    const int n_total = 2 * a.Cout;
     const uint32_t a_stages = (uint32_t)a.a_stages, b_stages = (uint32_t)a.b_stages;
     const int kchunks = a.kchunks;
     // unit i of this cluster -> (tile of this CTA, n tile)
@@ -526,7 +531,8 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (uint32_t i = 0; i < my_units; ++i) {
             int nt;
             (void)unit_tile(i, nt);
-            const int row0 = nt * a.n_tile + (int)rank * half;
+            // conv_tc packing: n tile T of 256 rows = 128 conv_f rows then 128 conv_m rows; this unit's channels start at nt * half
+            const int row0 = ((nt * half) >> 7) * 256 + (int)rank * 128 + ((nt * half) & 127);
             for (int kc = 0; kc < kchunks; ++kc) {
                 for (int tap = 0; tap < ntaps; ++tap) {
                     mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
@@ -586,7 +592,7 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     __syncwarp();
                     if (++as == a_stages) { as = 0; aph ^= 1u; }
                 }
-                if (++acc == 2u) { acc = 0; acc_ph ^= 1u; }
+                if (++acc == slots) { acc = 0; acc_ph ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -657,7 +663,7 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
-            if (++acc == 2u) { acc = 0; acc_ph ^= 1u; }
+            if (++acc == slots) { acc = 0; acc_ph ^= 1u; }
         }
     }
 
@@ -682,6 +688,8 @@ struct Tc2Plan {
     size_t smem_bytes;
     int kkn, epi, wide;
 };
+
+int g_tc_wide_ntile = 256;       // read_set_option "tc_wide_ntile": unit width of the streamed pair kernel for Cout = 256 (128: measured slower)
 
 bool tc2_supported(const read_conv_desc &d)
 {
@@ -711,7 +719,7 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     Tc2Plan *p = new (std::nothrow) Tc2Plan{};
     RB_CHECK_ARG(p != nullptr, "tcgen05 pair conv: out of host memory");
     const bool wide = d.Cin > 64;
-    const int cin_blk = wide ? 64 : d.Cin, n_tile = wide ? 256 : 2 * d.Cout;
+    const int cin_blk = wide ? 64 : d.Cin, n_tile = wide ? (g_tc_wide_ntile == 128 && d.Cout == 256 ? 128 : 256) : 2 * d.Cout;
     const int halo_rows = T2_TH + d.k - 1, halo_w = T2_TW + d.k - 1;
     const CUtensorMapSwizzle sw = cin_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
@@ -772,7 +780,8 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     a.a_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
     a.b_half_bytes = (uint32_t)(n_tile / 2) * cin_blk * 2u;
     a.kchunks = d.Cin / cin_blk;
-    a.nn_log2 = (2 * d.Cout) / n_tile == 2 ? 1 : 0;
+    a.nn_log2 = 0;
+    while ((n_tile << a.nn_log2) < 2 * d.Cout) ++a.nn_log2;
     a.elu = d.elu;
     a.bias_f = d.bias_f; a.bias_m = d.bias_m; a.scale = d.bn_scale; a.shift = d.bn_shift;
     a.residual = static_cast<const __nv_bfloat16 *>(d.residual);
@@ -780,7 +789,7 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
     p->kkn = cin_blk / 16;
     p->wide = wide ? 1 : 0;
     if (wide) {
-        a.slots = 2;
+        a.slots = T2_TMEM_COLS / n_tile;
         a.a_stages = 3;
         const size_t fixed = 1024 + 8 * S2_PARAMS + 16 * (size_t)d.Cout + 64;
         size_t left = 227 * 1024 - fixed - (size_t)a.a_stages * a.a_bytes;
