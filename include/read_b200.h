@@ -37,13 +37,17 @@ enum {
 
 int read_version(void);
 const char *read_last_error(void);
-/* Tuning options.  Results are bit-identical for every accepted setting; unknown names and out-of-range values are rejected.
+/* Tuning options.  Results are bit-identical for every accepted setting (one exception: "tc_pair_wide" selects a kernel whose K order
+ * differs - within one bf16 ulp per layer output); unknown names and out-of-range values are rejected.
  *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = auto), "raster_stream" (1),
  *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0)
  *   convs:      read when a plan is created: "tc_mt" (supertile width 1 (default) / 2 / 4, 0 = auto-widen), "tc_merge_done" (1),
- *               "tc_commit_late" (0), "tc_bpair" (0), "tc_probe" (0), "tc_pair" (1: CTA-pair cta_group::2 kernel for the Cin 64 layers,
- *               2: every eligible layer, 0: off); read at launch: "tc_role_rot" (1), "tc_pdl" (1: programmatic dependent
- *               launch between consecutive conv kernels)
+ *               "tc_commit_late" (0), "tc_bpair" (0), "tc_probe" (0), "tc_pair" (1: CTA-pair cta_group::2 kernel for the Cin 64 layers and
+ *               the Cin 32 layers without a residual, 2: every eligible layer, 0: off), "tc_pair_wide" (1: streamed-weight CTA-pair kernel for
+ *               the Cin, Cout = 128 / 256 layers), "tc_wide_ntile" (256; 128 = narrower units for Cout 256, measured slower),
+ *               "tc_tma_store" (1: epilogue items staged in shared memory and written by TMA stores; also read at launch by the pair kernel);
+ *               read at launch: "tc_role_rot" (1), "tc_pdl" (1: programmatic dependent launch between consecutive conv kernels)
+ *   The Python host applies READ_B200_OPTIONS="name=value,..." from the environment when it loads the library.
  * The options are process-wide tuning state (plain ints): set them before creating plans / launching, not concurrently with
  * launches from other threads.  Diagnostic knobs that skip work and therefore corrupt the output ("tc_debug", "tcg_debug",
  * raster_mode 4 / 5) exist only in builds compiled with -DREAD_DIAG and are absent from the shipped library. */

@@ -450,7 +450,7 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint8_t *smem_al = smem_raw + (smem_base - s_u32(smem_raw));
     constexpr int ntaps = KS * KS;
     const uint32_t b_region = smem_base + a.b_region_off;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + (uint32_t)a.b_stages * a.b_half_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + a.b_region_off + (uint32_t)a.b_stages * (uint32_t)KS * a.b_half_bytes);
     const uint32_t bar0 = s_u32(bars);
     const uint32_t afull0 = bar0 + 8 * S2_AFULL, aempty0 = bar0 + 8 * S2_AEMPTY, bfull0 = bar0 + 8 * S2_BFULL, bempty0 = bar0 + 8 * S2_BEMPTY;
     const uint32_t tfull0 = bar0 + 8 * S2_TFULL, tempty0 = bar0 + 8 * S2_TEMPTY;
@@ -534,11 +534,14 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             // conv_tc packing: n tile T of 256 rows = 128 conv_f rows then 128 conv_m rows; this unit's channels start at nt * half
             const int row0 = ((nt * half) >> 7) * 256 + (int)rank * 128 + ((nt * half) & 127);
             for (int kc = 0; kc < kchunks; ++kc) {
-                for (int tap = 0; tap < ntaps; ++tap) {
+                for (int ky = 0; ky < KS; ++ky) {                  // one stage = the KS taps of a filter row
                     mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
                     if (elect_one()) {
-                        if (leader) mbar_arrive_expect_tx(bfull0 + 8 * bs, 2u * a.b_half_bytes);
-                        tma2_load_2d(&tmB, (bfull0 + 8 * bs) & PEER_MASK, b_region + bs * a.b_half_bytes, 0, (tap * kchunks + kc) * n_total + row0);
+                        if (leader) mbar_arrive_expect_tx(bfull0 + 8 * bs, 2u * (uint32_t)KS * a.b_half_bytes);
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx)
+                            tma2_load_2d(&tmB, (bfull0 + 8 * bs) & PEER_MASK, b_region + (bs * (uint32_t)KS + (uint32_t)kx) * a.b_half_bytes, 0,
+                                         ((ky * KS + kx) * kchunks + kc) * n_total + row0);
                     }
                     __syncwarp();
                     if (++bs == b_stages) { bs = 0; bph ^= 1u; }
@@ -569,21 +572,23 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const uint32_t a_lo = a_lo0 + as * a16;
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
+                        // one weight stage = a filter row (KS taps, KS * KKN MMAs): with a stage per TAP the issuing thread's wait +
+                        // commit per four MMAs showed in the tensor pipe's duty cycle (80 %, profiles/r02_ncu_full.md)
+                        mbar_wait(bfull0 + 8 * bs, bph);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kx = 0; kx < KS; ++kx) {
-                            mbar_wait(bfull0 + 8 * bs, bph);
-                            tcgen05_fence_after();
-                            if (elect_one()) {
-                                const uint32_t bl = b_lo0 + bs * b16;
+                            for (int kx = 0; kx < KS; ++kx) {
+                                const uint32_t bl = b_lo0 + (bs * (uint32_t)KS + (uint32_t)kx) * b16;
                                 const uint32_t al = a_lo + (uint32_t)ky * ky_step + (uint32_t)kx * px16;
 #pragma unroll
                                 for (int kk = 0; kk < KKN; ++kk)
                                     umma2_bf16(d_tmem, al + 2u * kk, desc_hi, bl + 2u * kk, desc_hi_b, idesc, (kc | ky | kx | kk) != 0 ? 1u : 0u);
-                                umma2_commit_multicast(bempty0 + 8 * bs);
                             }
-                            __syncwarp();
-                            if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+                            umma2_commit_multicast(bempty0 + 8 * bs);
                         }
+                        __syncwarp();
+                        if (++bs == b_stages) { bs = 0; bph ^= 1u; }
                     }
                     if (elect_one()) {
                         umma2_commit_multicast(aempty0 + 8 * as);
@@ -793,16 +798,16 @@ int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out)
         a.a_stages = 3;
         const size_t fixed = 1024 + 8 * S2_PARAMS + 16 * (size_t)d.Cout + 64;
         size_t left = 227 * 1024 - fixed - (size_t)a.a_stages * a.a_bytes;
-        a.b_stages = (int)(left / a.b_half_bytes);
+        a.b_stages = (int)(left / ((size_t)d.k * a.b_half_bytes));          // a stage holds the k taps of one filter row
         if (a.b_stages > S2_MAX_B) a.b_stages = S2_MAX_B;
-        if (a.b_stages < 4) {
+        if (a.b_stages < 2) {
             set_error("tcgen05 pair conv: layer does not fit shared memory");
             delete p;
             return READ_ERR_UNSUPPORTED;
         }
         a.b_region_off = (uint32_t)a.a_stages * a.a_bytes;
         a.stage_off = 0;
-        p->smem_bytes = fixed + (size_t)a.a_stages * a.a_bytes + (size_t)a.b_stages * a.b_half_bytes;
+        p->smem_bytes = fixed + (size_t)a.a_stages * a.a_bytes + (size_t)a.b_stages * d.k * a.b_half_bytes;
         p->epi = 0;
         *out = p;
         return READ_OK;
