@@ -466,6 +466,8 @@ def run_ours(args):
     # every launch of the net timed IN SEQUENCE: the frame's launch order replayed eagerly on the launching stream with an event
     # between consecutive launches (host enqueue runs ahead of the GPU, so an interval = one kernel + its launch gap, in the cache
     # state the real frame sees); median of 3 replays after one warm replay
+    if hasattr(eng, "set_side_chain"):
+        eng.set_side_chain(False)            # per-layer timing: one stream, full grids
     n_ops = len(eng.ops)
     seq = np.zeros((4, n_ops))
     for r_ in range(4):

@@ -232,6 +232,9 @@ int read_pack_weights_tcg(const float *wf, const float *wm, int Cout, int Cin, i
 int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out);
 int read_conv_plan_launch(const read_conv_plan *p, void *stream);
 int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC / _TCGEN05 / _TCGEN05_GATHER */
+/* Cap the persistent grid of a tensor-core plan at max_ctas CTAs (0 = one per SM, the default): a caller that runs two independent
+ * layer chains on two streams gives each a share of the SMs so that both are resident at once (read_b200/engine.py). */
+int read_conv_plan_set_max_ctas(read_conv_plan *p, int max_ctas);
 void read_conv_plan_destroy(read_conv_plan *p);
 
 /* nn.Upsample(scale_factor=4, mode='bilinear') (unet.py:200), NHWC [B,h,w,C] -> [B,4h,4w,C], C % 8 == 0. */

@@ -42,6 +42,7 @@ struct read_conv_plan {
     int impl;
     TcPlan *tc;
     TcgPlan *tcg;
+    int max_ctas;            // 0 = one CTA per SM; > 0 caps the persistent grid (read_conv_plan_set_max_ctas)
 };
 
 static int validate_conv(const read_conv_desc &d)
@@ -140,7 +141,7 @@ int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out)
         RB_CHECK_ARG(d->w_generic != nullptr, "conv plan: generic kernel needs w_generic");
         RB_CHECK_ARG((reinterpret_cast<uintptr_t>(d->w_generic) & 15) == 0, "conv plan: w_generic must be 16B aligned");
     }
-    read_conv_plan *p = new (std::nothrow) read_conv_plan{*d, impl, nullptr, nullptr};
+    read_conv_plan *p = new (std::nothrow) read_conv_plan{*d, impl, nullptr, nullptr, 0};
     RB_CHECK_ARG(p != nullptr, "conv plan: out of host memory");
     if (impl == READ_CONV_TCGEN05) {
         rc = tc_plan_create(*d, &p->tc);
@@ -156,12 +157,19 @@ int read_conv_plan_create(const read_conv_desc *d, read_conv_plan **out)
 int read_conv_plan_launch(const read_conv_plan *p, void *stream)
 {
     RB_CHECK_ARG(p != nullptr, "conv plan: null plan");
-    if (p->impl == READ_CONV_TCGEN05) return tc_plan_launch(p->tc, (cudaStream_t)stream);
-    if (p->impl == READ_CONV_TCGEN05_GATHER) return tcg_plan_launch(p->tcg, (cudaStream_t)stream);
+    if (p->impl == READ_CONV_TCGEN05) return tc_plan_launch(p->tc, (cudaStream_t)stream, p->max_ctas);
+    if (p->impl == READ_CONV_TCGEN05_GATHER) return tcg_plan_launch(p->tcg, (cudaStream_t)stream, p->max_ctas);
     return launch_generic(p->d, (cudaStream_t)stream);
 }
 
 int read_conv_plan_impl(const read_conv_plan *p) { return p ? p->impl : 0; }
+
+int read_conv_plan_set_max_ctas(read_conv_plan *p, int max_ctas)
+{
+    RB_CHECK_ARG(p != nullptr && max_ctas >= 0, "conv plan: set_max_ctas needs a plan and a count >= 0");
+    p->max_ctas = max_ctas;
+    return READ_OK;
+}
 
 void read_conv_plan_destroy(read_conv_plan *p)
 {

@@ -71,7 +71,7 @@ int launch_generic(const read_conv_desc &d, cudaStream_t st);
 struct TcPlan;
 bool tc_supported(const read_conv_desc &d);
 int tc_plan_create(const read_conv_desc &d, TcPlan **out);
-int tc_plan_launch(const TcPlan *p, cudaStream_t st);
+int tc_plan_launch(const TcPlan *p, cudaStream_t st, int max_ctas = 0);     // max_ctas > 0: persistent grid of at most that many CTAs
 void tc_plan_destroy(TcPlan *p);
 
 
@@ -79,14 +79,14 @@ void tc_plan_destroy(TcPlan *p);
 struct Tc2Plan;
 bool tc2_supported(const read_conv_desc &d);
 int tc2_plan_create(const read_conv_desc &d, Tc2Plan **out);
-int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st);
+int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st, int max_ctas = 0);
 void tc2_plan_destroy(Tc2Plan *p);
 
 // tcgen05 path with gathered A operand (conv_tc_gather.cu)
 struct TcgPlan;
 bool tcg_supported(const read_conv_desc &d);
 int tcg_plan_create(const read_conv_desc &d, TcgPlan **out);
-int tcg_plan_launch(const TcgPlan *p, cudaStream_t st);
+int tcg_plan_launch(const TcgPlan *p, cudaStream_t st, int max_ctas = 0);
 void tcg_plan_destroy(TcgPlan *p);
 int64_t tcg_weight_elems(int Cout, int Cin, int k);
 int tcg_pack(const float *wf, const float *wm, int Cout, int Cin, int k, void *out, cudaStream_t st);

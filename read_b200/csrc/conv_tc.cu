@@ -1223,9 +1223,9 @@ unsigned long long *g_tc_trace = nullptr;    // READ_DIAG builds only (read_set_
 int g_tc_role_rot = 1;    // single-issuer roles in the highest warp ids (read_set_option "tc_role_rot")
 int g_tc_pdl = 1;         // programmatic dependent launch between consecutive conv kernels (read_set_option "tc_pdl")
 
-int tc_plan_launch(const TcPlan *p, cudaStream_t st)
+int tc_plan_launch(const TcPlan *p, cudaStream_t st, int max_ctas)
 {
-    if (p->pair != nullptr) return tc2_plan_launch(p->pair, st);
+    if (p->pair != nullptr) return tc2_plan_launch(p->pair, st, max_ctas);
     TcArgs a = p->args;
     a.debug = g_tc_debug;
     a.role_rot = g_tc_role_rot ? 1 : 0;
@@ -1234,6 +1234,7 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st)
     const long long total_tiles = (long long)a.stiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > total_tiles) grid = total_tiles;
     // cudaLaunchKernelEx with programmatic stream serialization: the kernel may be scheduled while its predecessor in the
     // stream drains; it calls griddepcontrol.wait before touching anything an earlier kernel produced (ptx.cuh: pdl_wait)

@@ -36,7 +36,7 @@ namespace rb {
             a.trace[(role_) * 2048] = ++trc_n;                                                                          \
         }                                                                                                               \
     } while (0)
-#define T2_DBG(a_, bit_) (((a_).debug & (bit_)) != 0)     // tc_debug: 2 = no global stores, 32 = no residual loads (timing experiments)
+#define T2_DBG(a_, bit_) (((a_).debug & (bit_)) != 0)     // tc_debug: 2 = no global stores, 32 = no residual loads, 64 = no TMA store / bulk-group instructions at all (timing experiments)
 #else
 #define T2_TRACE(role_, code_) do { } while (0)
 #define T2_DBG(a_, bit_) false
@@ -332,7 +332,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t kn = k + 1 == T2_NBUF ? 0u : k + 1;
             if (tma_out) {
                 if (lane == 0) {
-                    bulk_wait_group_read<1>();          // only the previous item's store may still be reading: buffers k and kn are free
+                    if (!T2_DBG(a, 64)) bulk_wait_group_read<1>();          // only the previous item's store may still be reading: buffers k and kn are free
                     if (has_res && it + item_step < my_units) {
                         const long long tn = t + 2ll * (long long)item_step * n_clusters;
                         const Tile2 tnc = decode2((int)tn, a);
@@ -365,6 +365,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) yv[j] = gate_folded<false>(__uint_as_float(f16[j]), __uint_as_float(m16[j]), par4[co + j]);
             }
+            T2_TRACE(trole, 10);
             if (tma_out) {
                 const uint32_t sb = sbuf0 + k * T2_STAGE_BYTES + lane_off;
                 if (has_res) {
@@ -383,9 +384,11 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int j = 0; j < 8; ++j) pk[j] = cvt2_bf16x2(yv[2 * j], yv[2 * j + 1]);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + sw), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (sw ^ 16u)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                T2_TRACE(trole, 11);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                T2_TRACE(trole, 12);
+                if (lane == 0 && !T2_DBG(a, 64)) {      // (64: timing experiment without any bulk-group bookkeeping)
                     if (!T2_DBG(a, 2)) tma_store_4d(&tmO, sbuf0 + k * T2_STAGE_BYTES, co, tc.tx * T2_TW, tc.ty * T2_TH + q * 4, b);
                     bulk_commit_group();
                 }
@@ -836,7 +839,7 @@ extern unsigned long long *g_tc_trace;
 extern int g_tc_debug;
 int g_tc_tma_store = 1;          // read_set_option "tc_tma_store": epilogue output through staged TMA stores (0: per-lane global stores)
 
-int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
+int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st, int max_ctas)
 {
     Tc2Args a = p->args;
     a.pdl = g_tc_pdl ? 1 : 0;
@@ -845,6 +848,7 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st)
     a.tma_out = g_tc_tma_store ? 1 : 0;
     if (a.n_tiles == 0) return READ_OK;
     long long grid = num_sms() & ~1;                  // whole pairs
+    if (max_ctas > 1 && grid > (max_ctas & ~1)) grid = max_ctas & ~1;
     const long long units = ((a.n_tiles + 1) / 2) << (p->wide ? a.nn_log2 : 0);
     if (grid > 2 * units) grid = 2 * units;
     cudaLaunchAttribute lattr[1];            // the cluster shape (2,1,1) is a compile-time attribute of the kernel

@@ -712,13 +712,14 @@ int tcg_plan_create(const read_conv_desc &d, TcgPlan **out)
 int g_tcg_debug = 0;
 extern int g_tc_pdl;
 
-int tcg_plan_launch(const TcgPlan *p, cudaStream_t st)
+int tcg_plan_launch(const TcgPlan *p, cudaStream_t st, int max_ctas)
 {
     GArgs a = p->args;
     a.debug = g_tcg_debug;
     const long long total_tiles = (long long)a.tiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
     long long grid = num_sms();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > total_tiles) grid = total_tiles;
     a.pdl = g_tc_pdl ? 1 : 0;
     cudaLaunchAttribute lattr[1];

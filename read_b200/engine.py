@@ -7,6 +7,8 @@ loader, ResBlock / FAM skip -> residual add in the epilogue, FAM product -> seco
 """
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -15,7 +17,7 @@ _MODE = {"id": L.SRC_IDENTITY, "down": L.SRC_NEAREST_DOWN, "up": L.SRC_NEAREST_U
 
 
 class _Layer:
-    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride", "kind", "cin", "cout")
+    __slots__ = ("name", "plan", "impl", "keep", "flops", "k", "stride", "kind", "cin", "cout", "side")
 
 
 class UNetEngine:
@@ -44,6 +46,16 @@ class UNetEngine:
         self.ops = []            # launch order: convs + auxiliary kernels (bilinear upsamples in bf16 mode)
         self._keep = []          # tensors the plans point into
         self.use_graph = use_graph
+        # Side chain (SURVEY.md §8f "small-layer tail"; OFF by default, READ_B200_SIDE_CHAIN=1): the SCM blocks of the two coarsest
+        # pyramid levels depend only on the net's inputs and are first consumed deep in the encoder, and each of their launches is a few
+        # tiles per SM - mostly pipeline fill and drain.  With the option they run on a second stream on SIDE_CTAS SMs while the main
+        # chain (the half-resolution SCM block, the first conv) runs on the rest; one event joins them before the first consumer; both
+        # chains are captured into the same CUDA graph.  Measured at C3 (scripts/ab_side.py, ABAB of whole-net graph replays,
+        # identical output): 5.84 ms without, 6.31 / 6.12 / 6.06 ms with 16 / 24 / 32 side SMs - the cross-stream graph edges cost the
+        # programmatic-dependent-launch overlap of ~10 launches and the main chain loses more on its smaller grids than the side
+        # chain hides.  Kept as a documented negative result.
+        self.side_chain = os.environ.get("READ_B200_SIDE_CHAIN", "0") == "1" and type(self) is UNetEngine
+        self._side_stream = None
         self.graph = None
         with torch.cuda.device(self.device):
             self._build()
@@ -157,6 +169,7 @@ class UNetEngine:
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
         ly.k, ly.stride, ly.kind = k, stride, "conv"
         ly.cin, ly.cout = cin, cout
+        ly.side = False
         self.layers.append(ly)
         self.ops.append(ly)
         self._after_conv(srcs, k, stride, out, out2, residual, out2_mul, addin, final)
@@ -236,6 +249,8 @@ class UNetEngine:
     def _build(self):
         self.inputs = self._make_inputs()
         self.output = self._build_graph(self.inputs)
+        if getattr(self, "_side_range", None) is not None:
+            self.set_side_chain(True)           # also caps the guard launches that follow the side range
         self.flops = sum(l.flops for l in self.layers)
         torch.cuda.current_stream().synchronize()   # weight packing done before any capture
 
@@ -247,8 +262,10 @@ class UNetEngine:
         c = self.base
         x, x2, x4, x8 = inputs
         z2 = self._scm("SCM2", x2, 2 * c)
+        n0 = len(self.ops)
         z4 = self._scm("SCM1", x4, 4 * c)
         z8 = self._scm("SCM0", x8, 8 * c)
+        self._mark_side(n0, len(self.ops))
         x_ = self._conv("feat_extract.0", [(x, "id", 1)], c, 3, 1, True)
         res1 = self._block("Encoder.0", x_, c)
         z = self._down_fam(1, "FAM2", res1, z2, 2 * c)
@@ -273,11 +290,80 @@ class UNetEngine:
         z = self._block("Decoder.3", z, c)
         return self._conv("feat_extract.5", [(z, "id", 1)], 3, 3, 1, False, final=True)
 
+    SIDE_CTAS = 24          # SMs of the side chain; the main-chain launches that overlap it use the rest
+
+    def _mark_side(self, i0, i1):
+        """ops[i0:i1] form the side chain; the main-chain ops before them (the half-resolution SCM block) and the first conv after
+        them share the device with it and get the complementary grid."""
+        if not (getattr(self, "side_chain", False) and self.bf16 and i1 > i0 and all(o.plan is not None for o in self.ops[i0:i1])):
+            return
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        if n_sm <= 2 * self.SIDE_CTAS:
+            return
+        for o in self.ops[i0:i1]:
+            o.side = True
+            L.check(self.lib.read_conv_plan_set_max_ctas(o.plan, self.SIDE_CTAS))
+        for o in self.ops[:i0]:
+            if o.plan is not None:
+                L.check(self.lib.read_conv_plan_set_max_ctas(o.plan, n_sm - self.SIDE_CTAS))
+        self._side_range = (i0, i1)
+        self._side_guard = 1      # main-chain launches after the side range that keep the reduced grid (the side chain may still run)
+
     # ------------------------------------------------------------------ execution
     def _launch_all(self):
         stream = L.stream_ptr()
-        for op in self.ops:
+        rng = getattr(self, "_side_range", None)
+        if rng is None:
+            for op in self.ops:
+                self.launch_op(op, stream)
+            return
+        i0, i1 = rng
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        fork = torch.cuda.Event()
+        fork.record(main)                      # the inputs were written on the main stream
+        side.wait_event(fork)
+        sptr = side.cuda_stream
+        for op in self.ops[i0:i1]:             # enqueue the side chain first: its CTAs take their SMs before the main chain's
+            self.launch_op(op, sptr)
+        join = torch.cuda.Event()
+        join.record(side)
+        for op in self.ops[:i0]:
             self.launch_op(op, stream)
+        joined = False
+        for op in self.ops[i1:]:
+            if not joined and self._reads_side_output(op):
+                main.wait_event(join)
+                joined = True
+            self.launch_op(op, stream)
+        if not joined:
+            main.wait_event(join)
+
+    def set_side_chain(self, on):
+        """Switch the two-stream schedule off (every launch on the current stream with a full grid: what per-layer timing wants)
+        or back on.  Drops a captured graph."""
+        rng = getattr(self, "_side_range_saved", None) or getattr(self, "_side_range", None)
+        if rng is None:
+            return
+        i0, i1 = rng
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        for j, o in enumerate(self.ops[:i1 + self._side_guard]):
+            if o.plan is not None:
+                cap = 0 if not on else (self.SIDE_CTAS if i0 <= j < i1 else n_sm - self.SIDE_CTAS)
+                L.check(self.lib.read_conv_plan_set_max_ctas(o.plan, cap))
+        self._side_range_saved = rng
+        self._side_range = rng if on else None
+        self.graph = None
+
+    def _reads_side_output(self, op):
+        """True if ``op`` consumes a tensor produced by the side chain (its ``keep`` list holds every tensor it touches)."""
+        i0, i1 = self._side_range
+        outs = getattr(self, "_side_outs", None)
+        if outs is None:
+            outs = self._side_outs = {id(t) for o in self.ops[i0:i1] for t in o.keep[6:8] if torch.is_tensor(t)}
+        return any(torch.is_tensor(t) and id(t) in outs for t in op.keep)
 
     def launch_op(self, op, stream=None):
         stream = L.stream_ptr() if stream is None else stream

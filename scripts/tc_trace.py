@@ -21,7 +21,7 @@ eng.run(); torch.cuda.synchronize()
 by = {ly.name: ly for ly in eng.layers}
 sp = L.stream_ptr()
 NAMES = {1: "P:empty ok", 2: "P:tma issued", 3: "I:tempty ok", 4: "I:afull ok", 5: "I:mma+commit issued", 6: "E:tfull ok", 7: "E:tmem ld done",
-         8: "E:item done", 9: "E:item start"}
+         8: "E:item done", 9: "E:item start", 10: "E:math done", 11: "E:sts done", 12: "E:fence+sync"}
 for n in names:
     buf = torch.zeros(32 * 2048, dtype=torch.int64, device=dev)
     eng.launch_op(by[n], sp); torch.cuda.synchronize()

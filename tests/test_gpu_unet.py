@@ -73,6 +73,23 @@ def test_engine_graph_replay_equals_eager(synth_sd):
     assert torch.equal(eng.output.cpu(), a)
 
 
+def test_side_chain_schedule_is_bit_identical(synth_sd, monkeypatch):
+    """READ_B200_SIDE_CHAIN=1 (SCM1 / SCM0 blocks on a second stream with capped grids, joined by an event; off by default): the
+    same kernels in a different schedule - the captured two-stream graph and the eager run equal the single-stream output."""
+    g = load_golden("net_64x64_b1")
+    feats = _golden_feats(g)
+    a, _ = _engine_out(synth_sd, feats, "bf16", graph=True)
+    monkeypatch.setenv("READ_B200_SIDE_CHAIN", "1")
+    b, eng = _engine_out(synth_sd, feats, "bf16", graph=True)
+    assert getattr(eng, "_side_range", None) is not None, "the side chain was not planned"
+    assert torch.equal(a, b)
+    eng.run(); eng.run()
+    torch.cuda.synchronize()
+    assert torch.equal(eng.output.cpu(), a)
+    c, _ = _engine_out(synth_sd, feats, "bf16", graph=False)
+    assert torch.equal(a, c)
+
+
 def test_engine_vs_oracle_larger_random_input(synth_sd):
     from oracle import unet_ref
     gen = torch.Generator().manual_seed(9)
