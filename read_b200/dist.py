@@ -77,6 +77,62 @@ def render_sharded(pyr, xyz_shard, id_base, total_m, group=None):
     return pyr
 
 
+class ShardedFrameStream:
+    """Throughput mode: ``world`` views per step, rank r refines view r, with the rasterizer ONE STEP AHEAD of
+    the net.  A step is: this rank's spatial tile rasterised for all ``world`` views in one pass, ONE reduce-scatter(min) of the
+    level-0 planes (rank r receives view r), fused resolve + gather into the net's inputs, the net.  The first three touch only the
+    pyramid and ``recv``; the net touches only its own buffers - so while the net of step i runs on the caller's stream, a side
+    stream already clears, rasterises and reduce-scatters step i+1 (``m_next``).  Per step the critical path is
+    max(gather + net, raster + collective) instead of their sum.
+
+    ``step(m_dev, m_next)``: m_dev / m_next are ``[world,4,4]`` device tensors (proj @ inv(view) per view); pass as ``m_next`` the
+    very tensor the next call will pass as ``m_dev`` (or None).  Returns the engine's output ``[1,3,H,W]`` for this rank's view."""
+
+    def __init__(self, store, tex_nd, engine, W, H, n_levels, layout, group=None):
+        from . import ops
+        self.ops, self.store, self.tex_nd, self.eng, self.layout, self.group = ops, store, tex_nd, engine, layout, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        dev = tex_nd.device
+        self.pyr = ops.Pyramid(self.world, W, H, n_levels, dev)
+        self.plane = W * H
+        self.recv = torch.empty(self.plane, dtype=torch.int64, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.rs_done, self.gather_done = torch.cuda.Event(), torch.cuda.Event()
+        self._pending = None                        # the matrices whose reduced plane is (being) produced into recv
+
+    def _raster_and_reduce(self, m_dev):
+        """On the CURRENT stream: clear level 0 of all views, one pass over the shard, reduce-scatter(min) into recv."""
+        from . import _lib as L
+        L.check(L.load().read_zbuf_clear(self.pyr.buf.data_ptr(), self.world * self.plane, L.stream_ptr()))
+        self.ops.raster_project_sorted(self.pyr, self.store, m_dev)
+        reduce_scatter_min_(self.recv, self.pyr.buf[:self.world * self.plane], self.group)
+
+    def step(self, m_dev, m_next=None):
+        cur = torch.cuda.current_stream()
+        if self._pending is None or self._pending.data_ptr() != m_dev.data_ptr():
+            start = torch.cuda.Event()
+            start.record(cur)
+            with torch.cuda.stream(self.side):      # no look-ahead for this step: do it now, still on the side stream (stream order
+                self.side.wait_event(start)         # after whatever look-ahead was in flight)
+                self._raster_and_reduce(m_dev)
+                self.rs_done.record(self.side)
+        cur.wait_event(self.rs_done)
+        r = self.rank
+        self.pyr.buf[r * self.plane:(r + 1) * self.plane].copy_(self.recv)
+        self.ops.pyramid_resolve_gather(self.tex_nd, self.pyr, self.eng.inputs, self.layout, view0=r, nviews=1)
+        self.gather_done.record(cur)
+        self._pending = None
+        if m_next is not None:
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.gather_done)       # the pyramid and recv are free again
+                self._raster_and_reduce(m_next)
+                self.rs_done.record(self.side)
+            m_next.record_stream(self.side)
+            self._pending = m_next
+        return self.eng.run()
+
+
 class StripFrameRenderer:
     """Latency mode: ``world`` GPUs cooperate on ONE frame.  Rank r rasterises its spatial tile of the
     scene, ONE all-reduce(min) makes the packed level-0 z-buffer complete on every rank, every rank gathers the feature pyramid
