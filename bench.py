@@ -402,7 +402,7 @@ def run_ours(args):
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         e2e_finish = lambda: torch.cuda.current_stream().wait_stream(copy_stream)
         e2e_h2d, e2e_d2h = 64, H * W * 4 * 4
-        e2e_note = ("FrameRenderer.infer(proj, view) per step: host numpy proj @ inv(view), pageable H2D of the 4x4 matrix, raster + gather + "
+        e2e_note = ("FrameRenderer.infer(proj, view) per step: host numpy proj @ inv(view), H2D of the 4x4 matrix through a pinned staging ring, raster + gather + "
                     "net + RGBA surface + net_input list, then D2H of the [H,W,4] f32 frame to pinned memory on a copy stream (double-buffered: the host "
                     "waits for frame i-1 while frame i renders; the last frame's copy is joined before the closing event); point cloud / "
                     "descriptors / weights are scene state resident in HBM (as MyRender.update_ds / load_textures)")

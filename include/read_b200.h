@@ -40,7 +40,8 @@ const char *read_last_error(void);
 /* Tuning options.  Results are bit-identical for every accepted setting (one exception: "tc_pair_wide" selects a kernel whose K order
  * differs - within one bf16 ulp per layer output); unknown names and out-of-range values are rejected.
  *   rasterizer: "raster_pipelined" (1), "raster_bulk_tma" (1), "raster_mode" (0..3, default 2), "raster_occupancy" (0 = auto), "raster_stream" (1),
- *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0)
+ *               "raster_dedup" (0), "raster_run" (0 = auto), "raster_nbr_filter" (0), "raster_stages" (2; 3 = deeper point ring),
+ *               "raster_carveout" (45: preferred shared-memory carveout in percent for the streaming kernel, -1 = driver default)
  *   convs:      read when a plan is created: "tc_mt" (supertile width 1 (default) / 2 / 4, 0 = auto-widen), "tc_merge_done" (1),
  *               "tc_commit_late" (0), "tc_bpair" (0), "tc_probe" (0), "tc_pair" (1: CTA-pair cta_group::2 kernel for the Cin 64 layers and
  *               the Cin 32 layers without a residual, 2: every eligible layer, 0: off), "tc_pair_wide" (1: streamed-weight CTA-pair kernel for

@@ -52,6 +52,24 @@ class FrameRenderer:
         self.return_net_input = bool(return_net_input)
         self.model.load_textures(0)
         self.model.to(self.device).eval()
+        # camera upload: a ring of pinned 4x4 staging buffers.  A pageable ``.to(device)`` blocks the host until the copy has run,
+        # and the copy is queued behind the previous frame's kernels - the host could not enqueue frame i+1 while frame i renders
+        # and the GPU idled for the host-side work of every frame (0.3 ms at C3).
+        self._cam_host = [torch.empty((1, 4, 4), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._cam_used = [None] * 4
+        self._cam_i = 0
+
+    def _upload_camera(self, total_m):
+        i = self._cam_i
+        self._cam_i = (i + 1) % len(self._cam_host)
+        if self._cam_used[i] is not None:
+            self._cam_used[i].synchronize()              # the copy that last read this staging buffer (4 frames ago) has run
+        self._cam_host[i].copy_(torch.from_numpy(total_m.reshape(1, 4, 4)))
+        m = self._cam_host[i].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._cam_used[i] = ev
+        return m
 
     @classmethod
     def from_checkpoints(cls, xyz, net_ckpt, texture_ckpt, viewport_size, **kw):
@@ -71,7 +89,7 @@ class FrameRenderer:
         """-> {'output': [H,W,4] f32 cuda tensor (RGB, alpha 1; flipped if ``flip_vertical``), 'net_input': list of the four
         [1,8,h,w] f32 net inputs (None with ``return_net_input=False``)} - the contract of ``OGL.infer`` (READ/gl/nn.py:113-129).
         Both are fresh tensors: the caller may keep them across frames, as with the reference."""
-        m = torch.from_numpy(self.total_matrix(proj_matrix, view_matrix).reshape(1, 4, 4)).to(self.device)
+        m = self._upload_camera(self.total_matrix(proj_matrix, view_matrix))
         with torch.no_grad():
             res = self.model.render(self.store if self.store is not None else self.xyz, m, self.W, self.H,
                                     n_levels=self.n_levels, return_input=self.return_net_input, clone_output=False)

@@ -25,8 +25,12 @@ def setopt(**kw):
 refs = []
 for m in mats:
     pyr.clear(); ops.raster_project(pyr, x0, m); torch.cuda.synchronize(); refs.append(pyr.buf.clone())
-variants = [("legacy", dict(raster_stream=0, raster_occupancy=0)), ("stream 4 CTA/SM", dict(raster_stream=1, raster_occupancy=4)),
-            ("stream 3 CTA/SM", dict(raster_stream=1, raster_occupancy=0)), ("stream 2 CTA/SM", dict(raster_stream=1, raster_occupancy=2))]
+variants = [("legacy", dict(raster_stream=0, raster_occupancy=0, raster_stages=3, raster_carveout=-1)),
+            ("stream 3 stages", dict(raster_stream=1, raster_occupancy=0, raster_stages=3, raster_carveout=-1)),
+            ("stream 2 stages", dict(raster_stream=1, raster_occupancy=0, raster_stages=2, raster_carveout=-1)),
+            ("stream 2 stages, carveout 45%", dict(raster_stream=1, raster_occupancy=0, raster_stages=2, raster_carveout=45)),
+            ("stream 3 stages, carveout 65%", dict(raster_stream=1, raster_occupancy=0, raster_stages=3, raster_carveout=65)),
+            ("stream 3 stages, carveout 100%", dict(raster_stream=1, raster_occupancy=0, raster_stages=3, raster_carveout=100))]
 times = {k: [] for k, _ in variants}
 bad = {k: 0 for k, _ in variants}
 for k, o in variants:
@@ -41,13 +45,13 @@ for rep in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); ops.raster_project_sorted(pyr, store, mats[0]); b.record(); torch.cuda.synchronize()
         times[k].append(a.elapsed_time(b) * 1e3)
-setopt(raster_stream=1, raster_occupancy=0)
+setopt(raster_stream=1, raster_occupancy=0, raster_stages=2, raster_carveout=45)
 rows = []
 for k, _ in variants:
     ts = sorted(times[k][2:])
     med = ts[len(ts) // 2]
     rows.append({"variant": k, "us_median": med, "us_best": ts[0], "store_GBps": 16 * N / (med * 1e-6) / 1e9, "mismatches": bad[k]})
-    print(f"{k:18s}: median {med:7.1f} us  best {ts[0]:7.1f} us  {16 * N / (med * 1e-6) / 1e9:7.1f} GB/s of the 16 B/point store  mismatching keys {bad[k]}")
+    print(f"{k:32s}: median {med:7.1f} us  best {ts[0]:7.1f} us  {16 * N / (med * 1e-6) / 1e9:7.1f} GB/s of the 16 B/point store  mismatching keys {bad[k]}")
 if len(sys.argv) > 1:
     json.dump(rows, open(sys.argv[1], "w"), indent=1)
 
