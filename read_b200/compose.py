@@ -21,6 +21,7 @@ import torch.nn as nn
 
 from . import ops
 from . import _lib as L
+from .texture import PointTexture
 
 
 def _as_id_list(texture_ids):
@@ -88,9 +89,40 @@ class NetAndTexture(nn.Module):
             scales.append(x)
         return scales
 
+    def _direct_engine_forward(self, maps, texture_ids):
+        """Inference shortcut of the index-map surface: one scene, four 'uv' maps and nothing else, no
+        supersampling / temporal average / autograd -> the descriptors are gathered from the index maps STRAIGHT into the engine's
+        NHWC inputs (same values as PointTexture.forward followed by the engine's NCHW f32 -> NHWC conversion: both round the same
+        f32 sample once) and the net runs; returns None when the call does not qualify."""
+        net = self.net
+        if (self.ss != 1 or self.temporal_average or net.training or getattr(net, '_is_replica', False) or len(set(texture_ids)) != 1
+                or len(maps) != 4 or not all('uv' in k for k in maps)):
+            return None
+        tex = self._texture(texture_ids[0])
+        if not isinstance(tex, PointTexture) or not tex.texture_.is_cuda or tex.texture_.shape[1] != 8:
+            return None
+        if torch.is_grad_enabled() and (tex.texture_.requires_grad or any(p.requires_grad for p in net.parameters())):
+            return None
+        vals = list(maps.values())
+        B, _, H, W = vals[0].shape
+        if len(texture_ids) != B or H % 16 or W % 16 or any(tuple(v.shape) != (B, 1, H >> l, W >> l) for l, v in enumerate(vals)):
+            return None
+        dev = tex.texture_.device
+        eng = net.engine(B, H, W, dev)
+        layout = L.FEAT_NHWC_BF16 if eng.bf16 else L.FEAT_NHWC_F32
+        nd = tex.point_major()
+        for l, v in enumerate(vals):
+            ids = v[:, 0].to(dev, torch.float32).contiguous()
+            ops.gather_from_index(nd, ids, layout, tex.activation, out=eng.inputs[l])
+        return eng.run().clone()
+
     def forward(self, inputs, **kwargs):
         maps = {k: v for k, v in inputs.items() if k != 'id'}
         texture_ids = _as_id_list(inputs['id'])
+        if not kwargs:
+            out = self._direct_engine_forward(maps, texture_ids)
+            if out is not None:
+                return out
         one_texture = len(set(texture_ids)) == 1
         if one_texture and len(texture_ids) > 1 and not self.temporal_average and not self.net.training:
             # eval-mode BatchNorm is per-pixel affine: B batch-1 passes == one batch-B pass

@@ -288,3 +288,57 @@ def test_frame_renderer_options_and_net_input(oracle_mod):
     assert c['net_input'] is None
     assert torch.equal(c['output'], a['output'])
     assert not torch.equal(r2.infer(proj[1], view[1])['output'], b['output'])       # frame 1 is blended with frame 0
+
+
+def test_index_map_surface_direct_engine_path_equals_module_path(synth_sd):
+    """NetAndTexture.forward's inference shortcut (descriptors gathered from the index maps straight into the engine's NHWC inputs)
+    returns exactly what the general path returns (PointTexture.forward -> UNet.forward), B = 1 and B = 2, with an activation."""
+    from read_b200.compose import NetAndTexture
+    from read_b200.texture import PointTexture
+    from read_b200.unet import UNet
+    n, H, W = 4000, 64, 96
+    gen = torch.Generator().manual_seed(9)
+    for act, B in (("none", 1), ("sigmoid", 2)):
+        net = UNet()
+        net.load_state_dict(synth_sd, strict=True)
+        tex = PointTexture(8, n, activation=act)
+        with torch.no_grad():
+            tex.texture_.copy_(torch.rand((1, 8, n), generator=gen) * 2 - 1)
+        model = NetAndTexture(net, {0: tex}, 1)
+        model.load_textures(0)
+        model.cuda().eval()
+        inp = {"id": torch.zeros(B, dtype=torch.long)}
+        for l in range(4):
+            ids = torch.randint(0, n, (B, 1, H >> l, W >> l), generator=gen).float()
+            inp["uv_1d_p1" + (f"_ds{l}" if l else "")] = ids.cuda()
+        with torch.no_grad():
+            fast = model(inp)
+            assert model._direct_engine_forward({k: v for k, v in inp.items() if k != "id"}, [0] * B) is not None
+            slow, _ = model(inp, return_input=True)              # kwargs -> the general path
+        assert fast.shape == (B, 3, H, W)
+        assert torch.equal(fast, slow)
+
+
+def test_sharded_frame_stream_lookahead_single_rank(synth_sd):
+    """dist.ShardedFrameStream without a process group (world 1): the rasterizer of step s+1 runs on the side stream under the net of
+    step s; every step's frame equals the plain sequence raster -> resolve/gather -> net.  (2 / 4 ranks: scripts/check_sharded_render.py.)"""
+    from read_b200 import dist as rdist
+    n, W, H = 60_000, 128, 64
+    d = dev()
+    store = ops.SortedPoints(torch.from_numpy(synth.street_scene(n, depth=60.0, seed=5)).to(d))
+    tex_nd = torch.rand((n, 8), device=d)
+    eng, eng1 = UNetEngine(synth_sd, 1, H, W, d), UNetEngine(synth_sd, 1, H, W, d)
+    sfs = rdist.ShardedFrameStream(store, tex_nd, eng, W, H, 4, L.FEAT_NHWC_BF16)
+    mats = [torch.from_numpy(synth.total_matrix(*synth.camera_batch(W, H, [p]))).to(d) for p in (0, 3, 6, 9, 12)]
+    one = ops.Pyramid(1, W, H, 4, d)
+    for s in range(4):
+        nxt = mats[s + 1] if s != 2 else None                     # step 3 arrives without a look-ahead: the stream must cope
+        out = sfs.step(mats[s], nxt).clone()
+        one.clear()
+        ops.raster_project_sorted(one, store, mats[s])
+        ops.pyramid_resolve_gather(tex_nd, one, eng1.inputs, L.FEAT_NHWC_BF16)
+        ref = eng1.run()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), f"step {s}"
+    torch.cuda.current_stream().wait_stream(sfs.side)
+    torch.cuda.synchronize()
