@@ -236,6 +236,10 @@ int read_conv_plan_impl(const read_conv_plan *p);   /* READ_CONV_GENERIC / _TCGE
 /* Cap the persistent grid of a tensor-core plan at max_ctas CTAs (0 = one per SM, the default): a caller that runs two independent
  * layer chains on two streams gives each a share of the SMs so that both are resident at once (read_b200/engine.py). */
 int read_conv_plan_set_max_ctas(read_conv_plan *p, int max_ctas);
+/* Tile traversal order of a tcgen05 TMA plan: 0 = top-down (default), 1 = bottom-up.  Same result.  A layer that walks the image in the
+ * opposite direction of its producer starts on the tiles the producer wrote LAST, i.e. the ones still in the 126 MB L2: consecutive
+ * layers of a chain alternate (read_b200/engine.py). */
+int read_conv_plan_set_tile_order(read_conv_plan *p, int reversed);
 void read_conv_plan_destroy(read_conv_plan *p);
 
 /* nn.Upsample(scale_factor=4, mode='bilinear') (unet.py:200), NHWC [B,h,w,C] -> [B,4h,4w,C], C % 8 == 0. */

@@ -102,6 +102,7 @@ _SIGS = {
     "read_conv_plan_launch": (c_int, [c_vp, c_vp]),
     "read_conv_plan_impl": (c_int, [c_vp]),
     "read_conv_plan_set_max_ctas": (c_int, [c_vp, c_int]),
+    "read_conv_plan_set_tile_order": (c_int, [c_vp, c_int]),
     "read_conv_plan_destroy": (None, [c_vp]),
     "read_upsample_bilinear4": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "read_frame_to_rgba": (c_int, [c_vp, c_int, c_int, c_int, ctypes.c_float, c_vp, c_vp]),

@@ -164,6 +164,13 @@ int read_conv_plan_launch(const read_conv_plan *p, void *stream)
 
 int read_conv_plan_impl(const read_conv_plan *p) { return p ? p->impl : 0; }
 
+int read_conv_plan_set_tile_order(read_conv_plan *p, int reversed)
+{
+    RB_CHECK_ARG(p != nullptr, "conv plan: set_tile_order needs a plan");
+    if (p->tc) tc_plan_set_reverse(p->tc, reversed);        // the gather / CUDA-core kernels keep their order
+    return READ_OK;
+}
+
 int read_conv_plan_set_max_ctas(read_conv_plan *p, int max_ctas)
 {
     RB_CHECK_ARG(p != nullptr && max_ctas >= 0, "conv plan: set_max_ctas needs a plan and a count >= 0");

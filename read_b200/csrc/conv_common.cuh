@@ -73,6 +73,7 @@ bool tc_supported(const read_conv_desc &d);
 int tc_plan_create(const read_conv_desc &d, TcPlan **out);
 int tc_plan_launch(const TcPlan *p, cudaStream_t st, int max_ctas = 0);     // max_ctas > 0: persistent grid of at most that many CTAs
 void tc_plan_destroy(TcPlan *p);
+void tc_plan_set_reverse(TcPlan *p, int reverse);      // walk the tiles bottom-up (same result; L2 reuse between consecutive layers)
 
 
 // tcgen05 CTA-pair path (conv_tc2.cu): cta_group::2 MMAs for the small-channel 3x3 layers

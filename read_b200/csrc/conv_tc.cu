@@ -116,6 +116,7 @@ struct TcArgs {
     int merge_done;                       // resident weights, kchunks == 1, mt == 1: ONE "tile done" commit per tile - the producers wait
                                           // on the accumulator's tfull barrier (A stage j of issuer me <-> accumulator slot 2j + me)
     int bpair;                            // streamed weights: one tcgen05.commit per PAIR of B stages
+    int rev_total;                        // 0, or the number of work units: unit t is mapped to rev_total - 1 - t (read_conv_plan_set_tile_order)
     int tma_out;                          // lean epilogue: items are staged in shared memory and written by TMA stores (plan: fits, no out2)
     uint32_t stage_bytes;                 // TC_STAGING_BYTES when the plan reserved the staging buffers (between the B region and the barriers)
     int probe;                            // issuers try_wait the NEXT tile's barriers before issuing the current tile's MMAs
@@ -130,6 +131,7 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(long long t, const TcArgs &a)
 {
     TileCoord c;
+    if (a.rev_total) t = (long long)a.rev_total - 1 - t;
     int mt = (int)t;
     c.nt = 0;
     if (a.n_tiles == 2) { c.nt = mt & 1; mt >>= 1; }
@@ -146,6 +148,7 @@ __device__ __forceinline__ TileCoord decode_supertile(int s, const TcArgs &a)
 {
     TileCoord c;
     c.nt = 0;
+    if (a.rev_total) s = a.rev_total - 1 - s;
     const int q = fdiv_small(s, a.inv_stx);
     c.tx = (s - q * a.stiles_x) * a.mt;
     c.b = fdiv_small(q, a.inv_ty);
@@ -995,6 +998,7 @@ struct TcPlan {
     TcArgs args;
     size_t smem_bytes;
     Tc2Plan *pair;           // CTA-pair variant (conv_tc2.cu) when the layer qualifies and "tc_pair" is on
+    int reverse;
 };
 
 int tc_plan_create(const read_conv_desc &d, TcPlan **out)
@@ -1233,6 +1237,7 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st, int max_ctas)
     a.trace = g_tc_trace;
     const long long total_tiles = (long long)a.stiles_x * a.tiles_y * a.B * a.n_tiles;
     if (total_tiles == 0) return READ_OK;
+    a.rev_total = p->reverse ? (int)total_tiles : 0;
     long long grid = num_sms();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > total_tiles) grid = total_tiles;
@@ -1303,6 +1308,13 @@ int tc_plan_launch(const TcPlan *p, cudaStream_t st, int max_ctas)
 #undef RB_TC_LAUNCH
     RB_LAUNCH_CHECK();
     return READ_OK;
+}
+
+void tc2_plan_set_reverse(Tc2Plan *p, int reverse);
+void tc_plan_set_reverse(TcPlan *p, int reverse)
+{
+    p->reverse = reverse ? 1 : 0;
+    if (p->pair) tc2_plan_set_reverse(p->pair, reverse);
 }
 
 void tc_plan_destroy(TcPlan *p)

@@ -65,6 +65,7 @@ struct Tc2Args {
     uint32_t b_region_off;
     uint32_t stage_off;                       // 16 warps x T2_NBUF x 1 KB staging buffers of the epilogue's TMA stores
     int elu, pdl, tma_out;
+    int reverse;                              // walk the units from the last to the first (read_conv_plan_set_tile_order)
     const float *bias_f, *bias_m, *scale, *shift;
     const __nv_bfloat16 *residual;
     __nv_bfloat16 *out;
@@ -208,6 +209,12 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const long long n_units = (a.n_tiles + 1) >> 1;
     const uint32_t my_units = (uint32_t)((n_units - cluster_id + n_clusters - 1) / n_clusters);   // same in both CTAs of the pair
     const uint32_t slots = (uint32_t)a.slots;
+    // unit i of this cluster -> this CTA's tile; a.reverse walks the image bottom-up (see read_conv_plan_set_tile_order)
+    auto tile_of = [&](uint32_t i) -> long long {
+        long long u = (long long)cluster_id + (long long)i * n_clusters;
+        if (a.reverse) u = n_units - 1 - u;
+        return 2ll * u + rank;
+    };
 
     if (warp == 0) {
         // ===================== TMA producer (one per CTA) =====================
@@ -221,7 +228,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (a.pdl) pdl_wait();                // activations come from the previous kernel; the (static) weights above do not
         uint32_t s = 0, ph = 0;
         for (uint32_t i = 0; i < my_units; ++i) {
-            const long long t = 2ll * ((long long)cluster_id + (long long)i * n_clusters) + rank;
+            const long long t = tile_of(i);
             const Tile2 tc = decode2((int)t, a);      // t >= n_tiles (odd tile count): b == B, the load is zero-filled
             mbar_wait(tfull0 + 8 * s, ph ^ 1u);       // stage free: the pair's MMAs of the tile that used it are complete
             T2_TRACE(rank * 8, 1);
@@ -315,13 +322,13 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t k = 0, kph = 0;                                                                      // staging buffer of this item
         const bool tma_out = a.tma_out != 0;
         if (tma_out && has_res && lane == 0 && ((uint32_t)sub >> lg) < my_units) {
-            const long long t0 = 2ll * ((long long)cluster_id + (long long)((uint32_t)sub >> lg) * n_clusters) + rank;
+            const long long t0 = tile_of((uint32_t)sub >> lg);
             const Tile2 t0c = decode2((int)t0, a);
             mbar_arrive_expect_tx(rfull0, T2_STAGE_BYTES);
             tma_load_4d(&tmR, rfull0, sbuf0, co, t0c.tx * T2_TW, t0c.ty * T2_TH + q * 4, t0c.b);
         }
         for (uint32_t it = (uint32_t)sub >> lg; it < my_units; it += item_step) {
-            const long long t = 2ll * ((long long)cluster_id + (long long)it * n_clusters) + rank;
+            const long long t = tile_of(it);
             const Tile2 tc = decode2((int)t, a);
             const int b = tc.b;
             const int x = tc.tx * T2_TW + px, y = tc.ty * T2_TH + py;
@@ -334,7 +341,7 @@ gated_conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (lane == 0) {
                     if (!T2_DBG(a, 64)) bulk_wait_group_read<1>();          // only the previous item's store may still be reading: buffers k and kn are free
                     if (has_res && it + item_step < my_units) {
-                        const long long tn = t + 2ll * (long long)item_step * n_clusters;
+                        const long long tn = tile_of(it + item_step);
                         const Tile2 tnc = decode2((int)tn, a);
                         mbar_arrive_expect_tx(rfull0 + 8 * kn, T2_STAGE_BYTES);
                         tma_load_4d(&tmR, rfull0 + 8 * kn, sbuf0 + kn * T2_STAGE_BYTES, co, tnc.tx * T2_TW, tnc.ty * T2_TH + q * 4, tnc.b);
@@ -504,7 +511,8 @@ gated_conv_tc2s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int kchunks = a.kchunks;
     // unit i of this cluster -> (tile of this CTA, n tile)
     auto unit_tile = [&](uint32_t i, int &nt) -> long long {
-        const long long u = (long long)cluster_id + (long long)i * n_clusters;
+        long long u = (long long)cluster_id + (long long)i * n_clusters;
+        if (a.reverse) u = n_units - 1 - u;
         nt = (int)(u & ((1 << nn_log2) - 1));
         return 2ll * (u >> nn_log2) + rank;
     };
@@ -695,6 +703,7 @@ struct Tc2Plan {
     Tc2Args args;
     size_t smem_bytes;
     int kkn, epi, wide;
+    int reverse;
 };
 
 int g_tc_wide_ntile = 256;       // read_set_option "tc_wide_ntile": unit width of the streamed pair kernel for Cout = 256 (128: measured slower)
@@ -846,6 +855,7 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st, int max_ctas)
     a.trace = g_tc_trace;
     a.debug = g_tc_debug;
     a.tma_out = g_tc_tma_store ? 1 : 0;
+    a.reverse = p->reverse;
     if (a.n_tiles == 0) return READ_OK;
     long long grid = num_sms() & ~1;                  // whole pairs
     if (max_ctas > 1 && grid > (max_ctas & ~1)) grid = max_ctas & ~1;
@@ -884,5 +894,6 @@ int tc2_plan_launch(const Tc2Plan *p, cudaStream_t st, int max_ctas)
 }
 
 void tc2_plan_destroy(Tc2Plan *p) { delete p; }
+void tc2_plan_set_reverse(Tc2Plan *p, int reverse) { p->reverse = reverse ? 1 : 0; }
 
 }  // namespace rb

@@ -46,6 +46,7 @@ class UNetEngine:
         self.ops = []            # launch order: convs + auxiliary kernels (bilinear upsamples in bf16 mode)
         self._keep = []          # tensors the plans point into
         self.use_graph = use_graph
+        self.alternate_order = os.environ.get("READ_B200_ALT_ORDER", "1") != "0"
         # Side chain (SURVEY.md §8f "small-layer tail"; OFF by default, READ_B200_SIDE_CHAIN=1): the SCM blocks of the two coarsest
         # pyramid levels depend only on the net's inputs and are first consumed deep in the encoder, and each of their launches is a few
         # tiles per SM - mostly pipeline fill and drain.  With the option they run on a second stream on SIDE_CTAS SMs while the main
@@ -164,6 +165,10 @@ class UNetEngine:
             keep.append(wg)
         plan = L.c_vp()
         L.check(lib.read_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
+        if self.alternate_order and (len(self.layers) & 1):
+            # consecutive launches walk the image in opposite directions: a layer starts on the tiles its producer wrote last,
+            # which are the ones still in L2 (every activation tensor of the two finest levels is larger than half the L2)
+            L.check(lib.read_conv_plan_set_tile_order(plan, 1))
         ly = _Layer()
         ly.name, ly.plan, ly.impl, ly.keep = (name or prefix), plan, lib.read_conv_plan_impl(plan), keep
         ly.flops = 2 * 2 * self.B * hout * wout * cout * cin * k * k
