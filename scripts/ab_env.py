@@ -1,5 +1,5 @@
 """ABAB of an engine-construction environment switch on whole-net CUDA-graph replays (C3 shapes) plus per-layer in-sequence times.
-   python scripts/ab_env.py READ_B200_ALT_ORDER 0 1"""
+   python scripts/ab_env.py READ_B200_ALT_ORDER 0 1      |      python scripts/ab_env.py opt:tc_pair 1 2"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,7 +15,10 @@ feats = [torch.rand((1, 8, H >> l, W >> l), generator=g) for l in range(4)]
 
 
 def mk(v):
-    os.environ[VAR] = v
+    if VAR.startswith("opt:"):               # a read_set_option read at plan creation, e.g. opt:tc_pair
+        L.check(L.load().read_set_option(VAR[4:].encode(), int(v)))
+    else:
+        os.environ[VAR] = v
     e = UNetEngine(sd, 1, H, W, dev, precision="bf16", use_graph=True)
     e.set_inputs_nchw([f.to(dev) for f in feats])
     for _ in range(3):
