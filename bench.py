@@ -343,7 +343,6 @@ def run_ours(args):
     mats_dev = mats_host.to(dev)
     frame_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     frame_host_rgb = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    recv = torch.empty(plane, dtype=torch.int64, device=dev) if world > 1 else None
 
     # N > 1: read_b200.dist.ShardedFrameStream - one pass over the shard for all views, ONE reduce-scatter (rank r gets view r), fused
     # resolve + gather, net; the rasterizer + collective of step s+1 run on a side stream under the net of step s
