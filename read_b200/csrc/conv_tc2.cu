@@ -19,6 +19,11 @@
 //                      A stage s free for both producers (A ring depth == accumulator ring depth, as conv_tc's merge_done)
 //   tempty (leader's)  slot s: both CTAs' epilogue items arrive (remote arrive from the peer) once their TMEM loads are done
 // Accumulators: cta_group::2 allocation, 128 lanes x N columns per tile in EACH CTA's TMEM at the same column offset.
+// Issue: warps 1 and 3 of the leader take alternate units; epilogue: 16 warps per CTA, items staged in shared memory and written by
+// TMA stores (residual tiles TMA-loaded one item ahead) - see the kernel.
+//
+// This file holds two kernels: gated_conv_tc2_kernel (weights resident: Cin 32 / 64) and, further down, gated_conv_tc2s_kernel
+// (weights streamed: Cin, Cout = 128 / 256, where the pair halves the L2 -> SM weight traffic per pixel).
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "ptx.cuh"
