@@ -131,6 +131,17 @@ def host_threads():
     return n
 
 
+def cpu_model():
+    """'model name' of the host CPU (print it next to the CPU timing)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def pick_torch_threads(sd):
     """torch's CPU convolutions do not scale to every core of a large shared host (oversubscription made a 128-thread
     run 25x slower than an 8-thread one): time one mid-size gated conv at a few thread counts and keep the fastest,
@@ -228,7 +239,7 @@ def run_reference_arm(args):
             "steps": steps, "warmup": warm_done, "ms_per_step": t_total / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": base_config(cfg),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "cpu": cpu_model(), "kind": "port", "sample": sample,
                              "raster_s": info["raster_s"], "gather_net_s": info["gather_net_s"]},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -630,7 +641,7 @@ def run_ours(args):
             oracle.build()
             cores, avail = pick_torch_threads(sd)
             t_frame, info, (oidx, odep), cpu_rgb = cpu_reference_frame(cfg, xyz_np, tex_cpu, sd, pose)
-            cpu_line = {"value": 1.0 / t_frame, "unit": "frames/s", "cores": cores, "kind": "port",
+            cpu_line = {"value": 1.0 / t_frame, "unit": "frames/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
                         "sample": (f"1 full frame of this workload, nothing extrapolated: sequential z-buffer (4 levels, {N_POINTS} pts, 1 thread/level) = "
                                    f"{info['raster_s']:.2f} s + gather + refinement net at {W}x{H} = {info['gather_net_s']:.2f} s; "
                                    f"torch threads {cores} (fastest of a sweep, {avail} available)")}
