@@ -32,7 +32,8 @@ def resample(t, mode, f):
     return F.interpolate(t, scale_factor=4, mode="bilinear", align_corners=False)
 
 
-def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=False, final=False, mul=False, seed=0):
+def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=False, final=False, mul=False, seed=0,
+             reversed_order=False):
     """srcs: list of (C, h, w, mode, factor) describing NCHW fp32 source tensors.  Returns (got, want[, got2, want2])."""
     lib = L.load()
     d = dev()
@@ -119,6 +120,8 @@ def run_conv(srcs, cout, k, stride, elu, act_bf16, impl, residual=False, out2=Fa
     plan = L.c_vp()
     L.check(lib.read_conv_plan_create(ctypes.byref(dsc), ctypes.byref(plan)))
     assert lib.read_conv_plan_impl(plan) == impl
+    if reversed_order:
+        L.check(lib.read_conv_plan_set_tile_order(plan, 1))
     L.check(lib.read_conv_plan_launch(plan, stream))
     torch.cuda.synchronize()
     lib.read_conv_plan_destroy(plan)
@@ -418,3 +421,27 @@ def test_tcgen05_cta_pair_matches_torch_and_the_single_cta_kernel(case):
         assert float((got - base).abs().max()) <= 2 ** -7 * float(want.abs().max())
     else:
         assert torch.equal(got, base)
+
+
+ORDER_CASES = [c for c in TC_CASES if not c[0].startswith("persistent C")][:24] + PAIR_CASES
+
+
+@pytest.mark.parametrize("case", ORDER_CASES, ids=[f"{i}: {c[0]}" for i, c in enumerate(ORDER_CASES)])
+def test_reversed_tile_order_is_bit_identical(case):
+    """read_conv_plan_set_tile_order(plan, 1) walks the tiles bottom-up (the engine alternates the direction between consecutive
+    layers for L2 reuse): same output bit for bit on every TMA kernel - single-CTA, CTA pair (odd tile counts: the phantom tile moves to
+    the other end) and streamed-weight pair."""
+    lib = L.load()
+    _, srcs, cout, k, elu, kw = case
+    kw = dict(kw)
+    stride = kw.pop("stride", 1)
+    try:
+        L.check(lib.read_set_option(b"tc_pair", 2))                      # pair kernels wherever they apply
+        fwd = run_conv(srcs, cout, k, stride, elu, True, TC, **kw)
+        rev = run_conv(srcs, cout, k, stride, elu, True, TC, reversed_order=True, **kw)
+    finally:
+        L.check(lib.read_set_option(b"tc_pair", 1))
+    assert torch.isfinite(rev[0]).all(), "outputs left unwritten (NaN sentinel)"
+    assert torch.equal(fwd[0], rev[0])
+    if kw.get("out2"):
+        assert torch.equal(fwd[2], rev[2])
